@@ -1,0 +1,769 @@
+// rtrb_api.cu — C ABI (include/rtrb_b200.h): scene baking, buffers, frame orchestration, the
+// resolve kernels (Camera#render_at's mean / variance test / final average, camera.rb:80-98, and
+// array_to_color, camera.rb:153-156), multi-GPU tile gather through peer mappings, and the FMA
+// issue microbenchmark used as the roofline denominator.
+//
+// Compiled with -fmad=false: the host-side baking and the resolve arithmetic must round exactly
+// like the reference's scalar FP64 code.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/rtrb_b200.h"
+#include "rtrb_launch.h"
+#include "rtrb_types.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(RTRB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- host FP64 vector helpers in the reference's evaluation order (fast_4d_matrix.c) -------------
+struct H3 { double x, y, z; };
+inline H3 h3(const double* p) { return H3{p[0], p[1], p[2]}; }
+inline double hnorm(H3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+inline H3 hnormalize(H3 a) { double r = hnorm(a); return H3{a.x / r, a.y / r, a.z / r}; }
+inline H3 hcross(H3 a, H3 b) { return H3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline H3 hadd(H3 a, H3 b) { return H3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline H3 hsub(H3 a, H3 b) { return H3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline H3 hmul(H3 a, double s) { return H3{a.x * s, a.y * s, a.z * s}; }
+inline void put(double* d, H3 a) { d[0] = a.x; d[1] = a.y; d[2] = a.z; }
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    if (want == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct rtrb_renderer {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // baked scene
+  int n_objects = 0, n_lights = 0;
+  double max_distance = 0, soft_shadow_exponent = 0;
+  DevBuf<DevGeom> geom;
+  DevBuf<DevMat> mat;
+  DevBuf<DevLight> lights;
+  std::vector<uint8_t*> textures;
+  // per-frame scratch
+  DevBuf<int32_t> tiles;
+  std::vector<int32_t> tiles_host;
+  int tiles_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  DevBuf<double> samples, extra_samples, rgb;
+  DevBuf<uint32_t> extra_list;
+  DevBuf<int32_t> hit;
+  DevBuf<uint8_t> rgba;
+  DevBuf<unsigned long long> counters;  // RTRB_CNT_N counters + [RTRB_CNT_N] first_bad
+  DevBuf<uint32_t> status;              // [0] status, [1] max stack, [2] extra_count
+  int fb_w = 0, fb_h = 0;
+  // last frame
+  int last_w = 0, last_h = 0;
+  bool last_has_rgb = false, last_has_hit = false;
+  cudaStream_t last_stream = nullptr;
+  bool timing_valid = false;
+};
+
+namespace {
+
+// ---- resolve kernels ---------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t quantise(double c) {  // camera.rb:153-156 + byte truncation
+  double x = c * 256.0;
+  double m = (255.0 < x) ? 255.0 : x;  // [x, 255].min
+  if (!(m > 0)) return 0;
+  return (uint8_t)(int)m;
+}
+
+__device__ __forceinline__ bool slot_to_xy(const FrameParams& P, uint32_t slot, int& x, int& y) {
+  uint32_t k = slot / RTRB_SUPER_PIXELS, q = slot % RTRB_SUPER_PIXELS;
+  int tile = P.tiles[k];
+  int qx, qy;
+  rtrb_morton_decode(q, &qx, &qy);
+  x = (tile % P.stx_count) * RTRB_SUPER + qx;
+  y = (tile / P.stx_count) * RTRB_SUPER + qy;
+  return x >= P.x0 && x < P.x1 && y >= P.y0 && y < P.y1;
+}
+
+__device__ __forceinline__ void write_pixel(const FrameParams& P, int x, int y, double r, double g, double b) {
+  size_t px = (size_t)y * P.width + x;
+  if (P.rgb) { P.rgb[px * 3 + 0] = r; P.rgb[px * 3 + 1] = g; P.rgb[px * 3 + 2] = b; }
+  uchar4 q = make_uchar4(quantise(r), quantise(g), quantise(b), 255);
+  reinterpret_cast<uchar4*>(P.rgba)[px] = q;
+}
+
+// mean of the pre samples in order, then the variance test (camera.rb:72-87)
+__device__ __forceinline__ void pre_mean(const FrameParams& P, uint32_t slot, double& ax, double& ay, double& az,
+                                         double& variance) {
+  const int S = P.pre;
+  const double* s = P.samples + (size_t)slot * S * 3;
+  ax = 0.0; ay = 0.0; az = 0.0;
+  for (int j = 0; j < S; ++j) { ax += s[j * 3 + 0]; ay += s[j * 3 + 1]; az += s[j * 3 + 2]; }
+  ax = ax / (double)S; ay = ay / (double)S; az = az / (double)S;
+  variance = 0;
+  for (int j = 0; j < S; ++j) {
+    double dx = s[j * 3 + 0] - ax, dy = s[j * 3 + 1] - ay, dz = s[j * 3 + 2] - az;
+    double m = fmax(dx, fmax(dy, dz));  // (sample - mean).to_a.max, signed
+    variance += m * m;
+  }
+  variance /= (double)S;
+}
+
+__global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ FrameParams P) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= (uint32_t)P.n_tiles * RTRB_SUPER_PIXELS) return;
+  int x, y;
+  if (!slot_to_xy(P, slot, x, y)) return;
+  double ax, ay, az, variance;
+  pre_mean(P, slot, ax, ay, az, variance);
+  if (variance >= P.variant_threshold) {
+    atomicAdd(&P.counters[RTRB_CNT_ADAPTIVE], 1ull);
+    if (P.max_samples > P.pre) {
+      uint32_t e = atomicAdd(P.extra_count, 1u);
+      P.extra_list[e] = slot;
+      return;  // finished by resolve_extra_kernel
+    }
+    // empty extra loop: (average * pre + 0) / max  (camera.rb:93)
+    const double fp = (double)P.pre, fm = (double)P.max_samples;
+    ax = (ax * fp + 0.0) / fm; ay = (ay * fp + 0.0) / fm; az = (az * fp + 0.0) / fm;
+  }
+  write_pixel(P, x, y, ax, ay, az);
+}
+
+__global__ void __launch_bounds__(256) resolve_extra_kernel(const __grid_constant__ FrameParams P) {
+  const uint32_t n = *P.extra_count;
+  const int E = P.max_samples - P.pre;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const uint32_t slot = P.extra_list[e];
+    int x, y;
+    if (!slot_to_xy(P, slot, x, y)) continue;
+    double ax, ay, az, variance;
+    pre_mean(P, slot, ax, ay, az, variance);
+    const double* s = P.extra_samples + (size_t)e * E * 3;
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    for (int j = 0; j < E; ++j) { cx += s[j * 3 + 0]; cy += s[j * 3 + 1]; cz += s[j * 3 + 2]; }
+    const double fp = (double)P.pre, fm = (double)P.max_samples;
+    ax = (ax * fp + cx) / fm; ay = (ay * fp + cy) / fm; az = (az * fp + cz) / fm;
+    write_pixel(P, x, y, ax, ay, az);
+  }
+}
+
+__global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---- FMA issue microbenchmark ------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+  T r0 = (T)threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+      r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+  }
+  T s = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
+  if (s == (T)-12345.678) out[0] = s;  // never true; keeps the chains alive
+}
+
+template <typename T>
+int measure_fma(int device, double* tflops_out) {
+  CUDA_TRY(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  T* d = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d, sizeof(T)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  fma_peak_kernel<T><<<blocks, threads>>>(d, 64, (T)1.0000001, (T)1e-9);  // warm-up
+  g_launches++;
+  CUDA_TRY(cudaDeviceSynchronize());
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    fma_peak_kernel<T><<<blocks, threads>>>(d, iters, (T)1.0000001, (T)1e-9);
+    g_launches++;
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops_out = best;
+  return RTRB_OK;
+}
+
+// ---- scene baking ------------------------------------------------------------------------------
+int validate_scene(const rtrb_scene_desc* s) {
+  if (!s) return fail(RTRB_ERR_INVALID, "scene is NULL");
+  if (s->n_objects < 0 || s->n_lights < 0 || s->n_textures < 0) return fail(RTRB_ERR_INVALID, "negative count");
+  if (s->n_lights > RTRB_MAX_LIGHTS) return fail(RTRB_ERR_UNSUPPORTED, "more than %d lights", RTRB_MAX_LIGHTS);
+  if (s->n_objects > 0 && !s->objects) return fail(RTRB_ERR_INVALID, "objects is NULL");
+  if (s->n_lights > 0 && !s->lights) return fail(RTRB_ERR_INVALID, "lights is NULL");
+  for (int i = 0; i < s->n_objects; ++i) {
+    const rtrb_object_desc& o = s->objects[i];
+    if (o.type != RTRB_OBJ_PLANE && o.type != RTRB_OBJ_SPHERE)
+      return fail(RTRB_ERR_UNSUPPORTED, "object %d: unknown type %d", i, o.type);
+    if (o.texture >= s->n_textures) return fail(RTRB_ERR_INVALID, "object %d: texture index out of range", i);
+    if (o.type == RTRB_OBJ_SPHERE && !o.has_refraction)
+      return fail(RTRB_ERR_INVALID, "object %d: a sphere needs refractive_rate (sphere.rb:93 divides unconditionally)", i);
+  }
+  for (int i = 0; i < s->n_textures; ++i)
+    if (!s->textures[i].rgb8 || s->textures[i].width <= 0 || s->textures[i].height <= 0)
+      return fail(RTRB_ERR_INVALID, "texture %d is empty", i);
+  return RTRB_OK;
+}
+
+int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
+  r->n_objects = s->n_objects;
+  r->n_lights = s->n_lights;
+  r->max_distance = s->max_distance;
+  r->soft_shadow_exponent = s->soft_shadow_exponent;
+  for (int i = 0; i < s->n_textures; ++i) {
+    const rtrb_texture_desc& t = s->textures[i];
+    uint8_t* d = nullptr;
+    size_t bytes = (size_t)t.width * t.height * 3;
+    CUDA_TRY(cudaMalloc((void**)&d, bytes));
+    r->textures.push_back(d);
+    CUDA_TRY(cudaMemcpy(d, t.rgb8, bytes, cudaMemcpyHostToDevice));
+  }
+  std::vector<DevGeom> geom(s->n_objects);
+  std::vector<DevMat> mat(s->n_objects);
+  for (int i = 0; i < s->n_objects; ++i) {
+    const rtrb_object_desc& o = s->objects[i];
+    DevGeom& g = geom[i];
+    DevMat& m = mat[i];
+    memset(&g, 0, sizeof(g));
+    memset(&m, 0, sizeof(m));
+    g.type = o.type;
+    g.px = o.point[0]; g.py = o.point[1]; g.pz = o.point[2];
+    g.radius = o.type == RTRB_OBJ_SPHERE ? o.radius : 0.0;
+    g.nx = o.front[0]; g.ny = o.front[1]; g.nz = o.front[2];
+    for (int k = 0; k < 3; ++k) {
+      m.diffuse[k] = o.diffuse_rate[k]; m.refl[k] = o.reflective_attenuation[k];
+      m.refr[k] = o.refractive_attenuation[k]; m.ambient[k] = o.ambient[k];
+    }
+    m.refractive_rate = o.refractive_rate;
+    m.has_refraction = o.has_refraction;
+    m.u_unit = o.u_unit; m.v_unit = o.v_unit;
+    m.hscale = o.texture_horizontal_scale; m.vscale = o.texture_vertical_scale;
+    m.uoff = o.texture_u_offset; m.voff = o.texture_v_offset;
+    if (o.texture >= 0) {
+      m.tex = r->textures[o.texture];
+      m.tex_w = s->textures[o.texture].width;
+      m.tex_h = s->textures[o.texture].height;
+      if (o.type == RTRB_OBJ_SPHERE) {
+        H3 gw = h3(o.greenwich_vec), np = h3(o.north_pole_vec);
+        H3 east = hcross(np, gw);  // sphere.rb:19
+        put(m.e0, hnormalize(gw)); put(m.e1, hnormalize(east)); put(m.e2, hnormalize(np));  // sphere.rb:113-115
+      } else {
+        H3 left = hnormalize(hcross(h3(o.front), h3(o.up)));  // plane.rb:21-23
+        put(m.e0, hnormalize(left));                          // plane.rb:82 normalises again
+        put(m.e1, hnormalize(h3(o.up)));
+      }
+    }
+  }
+  std::vector<DevLight> lights(s->n_lights);
+  for (int i = 0; i < s->n_lights; ++i) {
+    const rtrb_light_desc& l = s->lights[i];
+    DevLight& d = lights[i];
+    d.px = l.position[0]; d.py = l.position[1]; d.pz = l.position[2];
+    for (int k = 0; k < 3; ++k) {
+      d.color[k] = l.color[k];
+      d.color_hl[k] = l.color[k] * l.high_light_rate;  // world.rb:94
+    }
+    d.radius = l.radius;
+    d.hl_threshold = l.high_light_angle / 180.0 * 3.141592653589793;  // world.rb:92
+  }
+  CUDA_TRY(r->geom.ensure(std::max(1, s->n_objects)));
+  CUDA_TRY(r->mat.ensure(std::max(1, s->n_objects)));
+  CUDA_TRY(r->lights.ensure(std::max(1, s->n_lights)));
+  if (s->n_objects) {
+    CUDA_TRY(cudaMemcpy(r->geom.p, geom.data(), geom.size() * sizeof(DevGeom), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->mat.p, mat.data(), mat.size() * sizeof(DevMat), cudaMemcpyHostToDevice));
+  }
+  if (s->n_lights)
+    CUDA_TRY(cudaMemcpy(r->lights.p, lights.data(), lights.size() * sizeof(DevLight), cudaMemcpyHostToDevice));
+  return RTRB_OK;
+}
+
+// Camera#lens_func's per-frame constants in the reference's evaluation order (camera.rb:129-151).
+void bake_camera(FrameParams& P, const rtrb_camera_desc* c) {
+  H3 pos = h3(c->position), up = h3(c->up), front = h3(c->front);
+  H3 left = hnormalize(hcross(up, front));
+  H3 front_n = hnormalize(front);
+  put(P.pos, pos);
+  put(P.front, front);
+  put(P.left, left);
+  put(P.left_n, hnormalize(left));
+  put(P.up_n, hnormalize(up));
+  put(P.retina_center, hsub(pos, hmul(front_n, c->image_distance)));
+  double object_distance = c->focal_distance * c->image_distance / (c->image_distance - c->focal_distance);
+  put(P.focal_point, hadd(pos, hmul(front_n, object_distance)));
+  P.retina_width = c->retina_width; P.retina_height = c->retina_height;
+  P.aperture_radius = c->aperture_radius;
+  P.variant_threshold = c->variant_threshold;
+  P.width = c->width; P.height = c->height;
+  P.pre = c->pre_sample_times; P.max_samples = c->max_sample_times;
+  P.trace_depth = c->trace_depth; P.mc = c->monte_carlo_diffusion_times;
+}
+
+struct FrameTargets {  // where this renderer writes (own buffers, or rank 0's through a peer mapping)
+  uint8_t* rgba = nullptr;
+  double* rgb = nullptr;
+  int32_t* hit = nullptr;
+  bool want_rgb = true, want_hit = true;
+  bool no_fill = false;  // multi-GPU: the caller pre-fills, ranks must not race on the shared buffer
+};
+
+int ensure_framebuffers(rtrb_renderer* r, int w, int h, bool rgb, bool hit) {
+  size_t px = (size_t)w * h;
+  CUDA_TRY(cudaSetDevice(r->device));
+  if (r->rgba.n < px * 4) {
+    CUDA_TRY(r->rgba.ensure(px * 4));
+    CUDA_TRY(cudaMemset(r->rgba.p, 0, px * 4));
+  }
+  if (rgb) CUDA_TRY(r->rgb.ensure(px * 3));
+  if (hit) CUDA_TRY(r->hit.ensure(px));
+  r->fb_w = w; r->fb_h = h;
+  return RTRB_OK;
+}
+
+int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts_in,
+                const FrameTargets* targets, rtrb_stats* stats_out) {
+  if (!r || !cam) return fail(RTRB_ERR_INVALID, "renderer/camera is NULL");
+  rtrb_render_opts opts;
+  memset(&opts, 0, sizeof(opts));
+  if (opts_in) opts = *opts_in;
+  else { opts.seed = 1; opts.precision = RTRB_PREC_DEFAULT; }
+  if (cam->width <= 0 || cam->height <= 0) return fail(RTRB_ERR_INVALID, "bad frame size %dx%d", cam->width, cam->height);
+  if (cam->pre_sample_times < 1) return fail(RTRB_ERR_INVALID, "pre_sample_times must be >= 1");
+  if (cam->max_sample_times < 0 || cam->monte_carlo_diffusion_times < 0 || cam->trace_depth < 0)
+    return fail(RTRB_ERR_INVALID, "negative sampling parameter");
+  if (opts.rng_mode != RTRB_RNG_CTR)
+    return fail(RTRB_ERR_UNSUPPORTED, "rng_mode %d: only the counter RNG runs on the device (MT19937 is oracle-only)", opts.rng_mode);
+  if (opts.precision != RTRB_PREC_STRICT && opts.precision != RTRB_PREC_FAST64)
+    return fail(RTRB_ERR_INVALID, "unknown precision mode %d", opts.precision);
+  const int W = cam->width, H = cam->height;
+  int x0 = opts.x0, y0 = opts.y0, x1 = opts.x1, y1 = opts.y1;
+  if (x0 == 0 && y0 == 0 && x1 == 0 && y1 == 0) { x1 = W; y1 = H; }
+  if (x0 < 0 || y0 < 0 || x1 > W || y1 > H || x0 >= x1 || y0 >= y1) return fail(RTRB_ERR_INVALID, "bad window");
+  int world = opts.tile_world <= 1 ? 1 : opts.tile_world;
+  int rank = world == 1 ? 0 : opts.tile_rank;
+  if (rank < 0 || rank >= world) return fail(RTRB_ERR_INVALID, "tile_rank %d outside tile_world %d", rank, world);
+  const int stack_need = cam->trace_depth * (1 + cam->monte_carlo_diffusion_times) + 1;
+  if (stack_need > rtrb_max_stack_supported())
+    return fail(RTRB_ERR_UNSUPPORTED, "trace_depth*(1+mc)+1 = %d exceeds the device stack limit %d", stack_need,
+                rtrb_max_stack_supported());
+
+  CUDA_TRY(cudaSetDevice(r->device));
+  cudaStream_t stream = opts.stream ? (cudaStream_t)opts.stream : r->stream;
+
+  FrameTargets tg;
+  if (targets) tg = *targets;
+  {
+    int rc = ensure_framebuffers(r, W, H, tg.want_rgb && !tg.rgb, tg.want_hit && !tg.hit);
+    if (rc) return rc;
+  }
+  if (!tg.rgba) tg.rgba = opts.rgba_device_out ? (uint8_t*)opts.rgba_device_out : r->rgba.p;
+  if (tg.want_rgb && !tg.rgb) tg.rgb = r->rgb.p;
+  if (tg.want_hit && !tg.hit) tg.hit = r->hit.p;
+  if (!tg.want_rgb) tg.rgb = nullptr;
+  if (!tg.want_hit) tg.hit = nullptr;
+
+  // ---- tile list (cached) ----
+  const int stx_count = (W + RTRB_SUPER - 1) / RTRB_SUPER;
+  int key[8] = {W, H, x0, y0, x1, y1, rank, world};
+  if (memcmp(key, r->tiles_key, sizeof(key)) != 0) {
+    r->tiles_host.clear();
+    for (int ty = y0 / RTRB_SUPER; ty <= (y1 - 1) / RTRB_SUPER; ++ty)
+      for (int tx = x0 / RTRB_SUPER; tx <= (x1 - 1) / RTRB_SUPER; ++tx) {
+        int b = ty * stx_count + tx;
+        if (b % world == rank) r->tiles_host.push_back(b);
+      }
+    CUDA_TRY(r->tiles.ensure(std::max<size_t>(1, r->tiles_host.size())));
+    if (!r->tiles_host.empty())
+      CUDA_TRY(cudaMemcpyAsync(r->tiles.p, r->tiles_host.data(), r->tiles_host.size() * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    memcpy(r->tiles_key, key, sizeof(key));
+  }
+  const int n_tiles = (int)r->tiles_host.size();
+  const size_t n_slots = (size_t)n_tiles * RTRB_SUPER_PIXELS;
+  const int S = cam->pre_sample_times;
+  const int E = cam->max_sample_times > S ? cam->max_sample_times - S : 0;
+  if (n_slots * (size_t)S * 3 * sizeof(double) > ((size_t)96 << 30) || n_slots * (size_t)E * 3 * sizeof(double) > ((size_t)64 << 30))
+    return fail(RTRB_ERR_UNSUPPORTED, "sample buffer would exceed the per-frame memory budget");
+  CUDA_TRY(r->samples.ensure(std::max<size_t>(1, n_slots * S * 3)));
+  CUDA_TRY(r->extra_list.ensure(std::max<size_t>(1, n_slots)));
+  if (E > 0) CUDA_TRY(r->extra_samples.ensure(n_slots * E * 3));
+  CUDA_TRY(r->counters.ensure(RTRB_CNT_N + 1));
+  CUDA_TRY(r->status.ensure(4));
+
+  FrameParams P;
+  memset(&P, 0, sizeof(P));
+  bake_camera(P, cam);
+  P.max_distance = r->max_distance; P.soft_shadow_exponent = r->soft_shadow_exponent;
+  P.n_objects = r->n_objects; P.n_lights = r->n_lights;
+  P.geom = r->geom.p; P.mat = r->mat.p; P.lights = r->lights.p;
+  P.key0 = (uint32_t)opts.seed; P.key1 = (uint32_t)(opts.seed >> 32);
+  P.x0 = x0; P.y0 = y0; P.x1 = x1; P.y1 = y1;
+  P.n_tiles = n_tiles; P.stx_count = stx_count; P.tiles = r->tiles.p;
+  P.samples = r->samples.p; P.rgb = tg.rgb; P.hit = tg.hit; P.rgba = tg.rgba;
+  P.counters = r->counters.p; P.status = r->status.p; P.first_bad = r->counters.p + RTRB_CNT_N;
+  P.extra_count = r->status.p + 2; P.extra_list = r->extra_list.p; P.extra_samples = r->extra_samples.p;
+  P.count_detail = opts.count_detail;
+
+  const bool strict = opts.precision == RTRB_PREC_STRICT;
+  CUDA_TRY(cudaEventRecord(r->ev0, stream));
+  CUDA_TRY(cudaMemsetAsync(r->counters.p, 0, RTRB_CNT_N * sizeof(unsigned long long), stream));
+  CUDA_TRY(cudaMemsetAsync(r->counters.p + RTRB_CNT_N, 0xff, sizeof(unsigned long long), stream));
+  CUDA_TRY(cudaMemsetAsync(r->status.p, 0, 4 * sizeof(uint32_t), stream));
+  const bool partial = !(x0 == 0 && y0 == 0 && x1 == W && y1 == H && world == 1);
+  if (partial && !tg.no_fill && tg.hit == r->hit.p && tg.hit) {
+    size_t n = (size_t)W * H;
+    fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tg.hit, n, -3);
+    g_launches++;
+  }
+  if (n_tiles > 0) {
+    CUDA_TRY(strict ? rtrb_launch_trace_pre_strict(P, stack_need, stream) : rtrb_launch_trace_pre_fast(P, stack_need, stream));
+    g_launches++;
+    resolve_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    if (E > 0) {
+      CUDA_TRY(strict ? rtrb_launch_trace_extra_strict(P, stack_need, stream) : rtrb_launch_trace_extra_fast(P, stack_need, stream));
+      g_launches++;
+      resolve_extra_kernel<<<296, 256, 0, stream>>>(P);
+      CUDA_TRY(cudaGetLastError());
+      g_launches++;
+    }
+  }
+  CUDA_TRY(cudaEventRecord(r->ev1, stream));
+  r->last_w = W; r->last_h = H;
+  r->last_has_rgb = tg.rgb == r->rgb.p && tg.rgb != nullptr;
+  r->last_has_hit = tg.hit == r->hit.p && tg.hit != nullptr;
+  r->last_stream = stream;
+
+  if (stats_out) {
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    unsigned long long c[RTRB_CNT_N + 1];
+    uint32_t st[4];
+    CUDA_TRY(cudaMemcpy(c, r->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(st, r->status.p, sizeof(st), cudaMemcpyDeviceToHost));
+    memset(stats_out, 0, sizeof(*stats_out));
+    stats_out->samples = opts.count_detail ? c[RTRB_CNT_SAMPLES] : 0;
+    stats_out->rays = c[RTRB_CNT_RAYS]; stats_out->shadow_queries = c[RTRB_CNT_SHADOW];
+    stats_out->highlight_hits = c[RTRB_CNT_HIGHLIGHT]; stats_out->hits = c[RTRB_CNT_HITS];
+    stats_out->local_shaded = c[RTRB_CNT_LOCAL]; stats_out->lit_lights = c[RTRB_CNT_LIT];
+    stats_out->mc_rays = c[RTRB_CNT_MC]; stats_out->refractions = c[RTRB_CNT_REFR];
+    stats_out->texel_fetches = c[RTRB_CNT_TEXEL];
+    stats_out->sphere_tests = c[RTRB_CNT_SPH_TEST]; stats_out->sphere_accepts = c[RTRB_CNT_SPH_ACC];
+    stats_out->plane_tests = c[RTRB_CNT_PL_TEST]; stats_out->plane_accepts = c[RTRB_CNT_PL_ACC];
+    stats_out->cover_sphere = c[RTRB_CNT_COV_SPH]; stats_out->cover_sphere_full = c[RTRB_CNT_COV_SPH_FULL];
+    stats_out->cover_sphere_penumbra = c[RTRB_CNT_COV_SPH_PEN];
+    stats_out->cover_plane = c[RTRB_CNT_COV_PL]; stats_out->cover_plane_accepts = c[RTRB_CNT_COV_PL_ACC];
+    stats_out->adaptive_pixels = c[RTRB_CNT_ADAPTIVE]; stats_out->exact_tests = c[RTRB_CNT_EXACT];
+    if (!opts.count_detail) {
+      // samples are a pure function of the window when nothing is adaptive; otherwise count_detail reports them
+      size_t px = 0;
+      for (int b : r->tiles_host) {
+        int tx = b % stx_count, ty = b / stx_count;
+        int ax0 = std::max(x0, tx * RTRB_SUPER), ax1 = std::min(x1, (tx + 1) * RTRB_SUPER);
+        int ay0 = std::max(y0, ty * RTRB_SUPER), ay1 = std::min(y1, (ty + 1) * RTRB_SUPER);
+        if (ax1 > ax0 && ay1 > ay0) px += (size_t)(ax1 - ax0) * (ay1 - ay0);
+      }
+      stats_out->samples = (uint64_t)px * S + (uint64_t)(E > 0 ? c[RTRB_CNT_ADAPTIVE] * (uint64_t)E : 0);
+    }
+    stats_out->status = st[0];
+    stats_out->max_stack = st[1];
+    if (st[0] && c[RTRB_CNT_N] != ~0ull) {
+      stats_out->first_bad_x = (int32_t)(c[RTRB_CNT_N] / (unsigned long long)H);
+      stats_out->first_bad_y = (int32_t)(c[RTRB_CNT_N] % (unsigned long long)H);
+    } else {
+      stats_out->first_bad_x = stats_out->first_bad_y = -1;
+    }
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
+    stats_out->device_ms = ms;
+    if (st[0]) {
+      fail(RTRB_ERR_RAISED, "the reference would have raised: status 0x%x at pixel (%d, %d)", st[0],
+           stats_out->first_bad_x, stats_out->first_bad_y);
+      return RTRB_ERR_RAISED;
+    }
+  }
+  return RTRB_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+#pragma GCC visibility push(default)
+
+int rtrb_abi_version(void) { return RTRB_ABI_VERSION; }
+const char* rtrb_last_error(void) { return g_last_error.c_str(); }
+uint64_t rtrb_launch_count(void) { return g_launches.load(); }
+
+int rtrb_device_count(int* count_out) {
+  if (!count_out) return fail(RTRB_ERR_INVALID, "count_out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count_out = 0; return fail(RTRB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+  *count_out = n;
+  return RTRB_OK;
+}
+
+int rtrb_renderer_create(const rtrb_scene_desc* scene, int device, rtrb_renderer** out) {
+  if (!out) return fail(RTRB_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = validate_scene(scene);
+  if (rc) return rc;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(RTRB_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(RTRB_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  CUDA_TRY(cudaSetDevice(device));
+  rtrb_renderer* r = new rtrb_renderer();
+  r->device = device;
+  cudaError_t ce;
+  if ((ce = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (ce = cudaEventCreate(&r->ev0)) != cudaSuccess || (ce = cudaEventCreate(&r->ev1)) != cudaSuccess) {
+    delete r;
+    return fail(RTRB_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(ce));
+  }
+  rc = bake_scene(r, scene);
+  if (rc) { rtrb_renderer_destroy(r); return rc; }
+  *out = r;
+  return RTRB_OK;
+}
+
+int rtrb_renderer_destroy(rtrb_renderer* r) {
+  if (!r) return RTRB_OK;
+  cudaSetDevice(r->device);
+  cudaDeviceSynchronize();
+  r->geom.release(); r->mat.release(); r->lights.release(); r->tiles.release(); r->samples.release();
+  r->extra_samples.release(); r->rgb.release(); r->extra_list.release(); r->hit.release(); r->rgba.release();
+  r->counters.release(); r->status.release();
+  for (uint8_t* t : r->textures) cudaFree(t);
+  if (r->ev0) cudaEventDestroy(r->ev0);
+  if (r->ev1) cudaEventDestroy(r->ev1);
+  if (r->stream) cudaStreamDestroy(r->stream);
+  delete r;
+  return RTRB_OK;
+}
+
+int rtrb_render_device(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts,
+                       rtrb_stats* stats_out) {
+  return render_impl(r, cam, opts, nullptr, stats_out);
+}
+
+int rtrb_download(rtrb_renderer* r, uint8_t* rgba, double* rgb_or_null, int32_t* hit_or_null) {
+  if (!r) return fail(RTRB_ERR_INVALID, "renderer is NULL");
+  if (r->last_w == 0) return fail(RTRB_ERR_INVALID, "nothing rendered yet");
+  CUDA_TRY(cudaSetDevice(r->device));
+  cudaStream_t s = r->last_stream ? r->last_stream : r->stream;
+  size_t px = (size_t)r->last_w * r->last_h;
+  if (rgba) CUDA_TRY(cudaMemcpyAsync(rgba, r->rgba.p, px * 4, cudaMemcpyDeviceToHost, s));
+  if (rgb_or_null) {
+    if (!r->last_has_rgb) return fail(RTRB_ERR_INVALID, "the last frame kept no float RGB");
+    CUDA_TRY(cudaMemcpyAsync(rgb_or_null, r->rgb.p, px * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  if (hit_or_null) {
+    if (!r->last_has_hit) return fail(RTRB_ERR_INVALID, "the last frame kept no hit ids");
+    CUDA_TRY(cudaMemcpyAsync(hit_or_null, r->hit.p, px * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return RTRB_OK;
+}
+
+int rtrb_render(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts, uint8_t* rgba,
+                double* rgb_or_null, int32_t* hit_or_null, rtrb_stats* stats_out) {
+  if (!rgba) return fail(RTRB_ERR_INVALID, "rgba is NULL");
+  FrameTargets tg;
+  tg.want_rgb = rgb_or_null != nullptr;
+  tg.want_hit = hit_or_null != nullptr;
+  rtrb_stats local;
+  int rc = render_impl(r, cam, opts, &tg, stats_out ? stats_out : &local);
+  if (rc != RTRB_OK && rc != RTRB_ERR_RAISED) return rc;
+  std::string keep = g_last_error;
+  int rc2 = rtrb_download(r, rgba, rgb_or_null, hit_or_null);
+  if (rc2) return rc2;
+  if (rc == RTRB_ERR_RAISED) g_last_error = keep;
+  return rc;
+}
+
+int rtrb_framebuffer_device_ptr(rtrb_renderer* r, int width, int height, void** ptr_out) {
+  if (!r || !ptr_out || width <= 0 || height <= 0) return fail(RTRB_ERR_INVALID, "bad argument");
+  int rc = ensure_framebuffers(r, width, height, false, false);
+  if (rc) return rc;
+  *ptr_out = r->rgba.p;
+  return RTRB_OK;
+}
+
+int rtrb_framebuffer_ipc_export(rtrb_renderer* r, int width, int height, uint8_t handle_out[64]) {
+  if (!r || !handle_out) return fail(RTRB_ERR_INVALID, "bad argument");
+  int rc = ensure_framebuffers(r, width, height, false, false);
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, r->rgba.p));
+  memcpy(handle_out, &h, 64);
+  return RTRB_OK;
+}
+
+int rtrb_ipc_open(int device, const uint8_t handle[64], void** ptr_out) {
+  if (!handle || !ptr_out) return fail(RTRB_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return RTRB_OK;
+}
+
+int rtrb_ipc_close(int device, void* ptr) {
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return RTRB_OK;
+}
+
+int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_desc* cam,
+                      const rtrb_render_opts* opts_in, uint8_t* rgba, double* rgb_or_null, int32_t* hit_or_null,
+                      rtrb_stats* stats_out) {
+  if (!renderers || n < 1 || !cam || !rgba) return fail(RTRB_ERR_INVALID, "bad argument");
+  if (n == 1) return rtrb_render(renderers[0], cam, opts_in, rgba, rgb_or_null, hit_or_null, stats_out);
+  rtrb_renderer* root = renderers[0];
+  const bool want_rgb = rgb_or_null != nullptr, want_hit = hit_or_null != nullptr;
+  int rc = ensure_framebuffers(root, cam->width, cam->height, want_rgb, want_hit);
+  if (rc) return rc;
+  // peer access root <- others (writes land in root's framebuffer over NVLink; no collective)
+  for (int i = 1; i < n; ++i) {
+    int can = 0;
+    CUDA_TRY(cudaDeviceCanAccessPeer(&can, renderers[i]->device, root->device));
+    if (!can) return fail(RTRB_ERR_CUDA, "device %d cannot access device %d", renderers[i]->device, root->device);
+    CUDA_TRY(cudaSetDevice(renderers[i]->device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(root->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+      return fail(RTRB_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  rtrb_render_opts base;
+  memset(&base, 0, sizeof(base));
+  if (opts_in) base = *opts_in;
+  else { base.seed = 1; base.precision = RTRB_PREC_DEFAULT; }
+  {
+    const rtrb_render_opts& b = base;
+    const bool full = (b.x0 == 0 && b.y0 == 0 && b.x1 == 0 && b.y1 == 0) ||
+                      (b.x0 == 0 && b.y0 == 0 && b.x1 == cam->width && b.y1 == cam->height);
+    if (!full && want_hit) {
+      CUDA_TRY(cudaSetDevice(root->device));
+      size_t npx = (size_t)cam->width * cam->height;
+      fill_i32_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, root->stream>>>(root->hit.p, npx, -3);
+      g_launches++;
+      CUDA_TRY(cudaStreamSynchronize(root->stream));
+    }
+  }
+  std::vector<rtrb_stats> st(n);
+  std::vector<int> rcs(n, 0);
+  std::vector<std::string> errs(n);
+  std::vector<std::thread> th;
+  for (int i = 0; i < n; ++i) {
+    th.emplace_back([&, i]() {
+      rtrb_render_opts o = base;
+      o.tile_rank = i; o.tile_world = n; o.stream = nullptr; o.rgba_device_out = nullptr;
+      FrameTargets tg;
+      tg.rgba = root->rgba.p;
+      tg.rgb = want_rgb ? root->rgb.p : nullptr;
+      tg.hit = want_hit ? root->hit.p : nullptr;
+      tg.want_rgb = want_rgb; tg.want_hit = want_hit; tg.no_fill = true;
+      rcs[i] = render_impl(renderers[i], cam, &o, &tg, &st[i]);
+      errs[i] = g_last_error;
+    });
+  }
+  for (auto& t : th) t.join();
+  int worst = RTRB_OK;
+  for (int i = 0; i < n; ++i) {
+    if (rcs[i] != RTRB_OK && rcs[i] != RTRB_ERR_RAISED) { g_last_error = errs[i]; return rcs[i]; }
+    if (rcs[i] == RTRB_ERR_RAISED) { worst = RTRB_ERR_RAISED; g_last_error = errs[i]; }
+  }
+  rtrb_stats agg;
+  memset(&agg, 0, sizeof(agg));
+  agg.first_bad_x = agg.first_bad_y = -1;
+  long long best_key = -1;
+  {
+    uint64_t* a = &agg.samples;
+    for (int i = 0; i < n; ++i) {
+      const uint64_t* b = &st[i].samples;
+      for (int k = 0; k < 21; ++k) a[k] += b[k];
+      agg.status |= st[i].status;
+      agg.max_stack = std::max(agg.max_stack, st[i].max_stack);
+      agg.device_ms = std::max(agg.device_ms, st[i].device_ms);
+      if (st[i].first_bad_x >= 0) {
+        long long key = (long long)st[i].first_bad_x * cam->height + st[i].first_bad_y;
+        if (best_key < 0 || key < best_key) { best_key = key; agg.first_bad_x = st[i].first_bad_x; agg.first_bad_y = st[i].first_bad_y; }
+      }
+    }
+  }
+  if (stats_out) *stats_out = agg;
+  root->last_w = cam->width; root->last_h = cam->height;
+  root->last_has_rgb = want_rgb; root->last_has_hit = want_hit;
+  root->last_stream = root->stream;
+  std::string keep = g_last_error;
+  rc = rtrb_download(root, rgba, rgb_or_null, hit_or_null);
+  if (rc) return rc;
+  if (worst == RTRB_ERR_RAISED) g_last_error = keep;
+  return worst;
+}
+
+int rtrb_measure_fma_peak(int device, int which, double* tflops_out) {
+  if (!tflops_out) return fail(RTRB_ERR_INVALID, "tflops_out is NULL");
+  return which == 0 ? measure_fma<float>(device, tflops_out) : measure_fma<double>(device, tflops_out);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,554 @@
+// rtrb_trace.cuh — the ray-tree engine of raytracing_rb as device code (sm_100a).
+//
+// One thread owns one pixel-sample: it builds the thin-lens primary ray (camera.rb:129-151), then
+// runs RayTracer#trace_sync (ray_tracer.rb:16-46) with the work stack as an explicit per-thread
+// LIFO array in local memory, popping the LAST pushed item exactly like `@queue.pop` (:32), and
+// accumulates the colours in emission order (rt_reduce, :292-298).
+//
+// STRICT arithmetic contract: this translation unit is compiled with -fmad=false and every
+// expression keeps the reference's association order, every division and square root the
+// reference performs is performed, so FP64 results equal the CPU oracle's bit for bit except where
+// libm's transcendental functions (sin cos acos asin pow) round differently from CUDA's.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/rtrb_b200.h"
+#include "rtrb_types.h"
+
+namespace rtrb {
+
+#define RTRB_EPSILON 1e-5                 // src/libs/algebra.rb:2
+#define RTRB_PI 3.141592653589793         // Math::PI
+
+struct d3 { double x, y, z; };
+
+__device__ __forceinline__ d3 mk(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ d3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
+__device__ __forceinline__ d3 operator+(d3 a, d3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ d3 operator-(d3 a, d3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ d3 operator-(d3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ d3 operator*(d3 a, d3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ d3 operator*(d3 a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ d3 operator/(d3 a, double s) { return mk(a.x / s, a.y / s, a.z / s); }
+// Vec3_method_dot (fast_4d_matrix.c:98-108): ((a0*b0) + a1*b1) + a2*b2
+__device__ __forceinline__ double dot(d3 a, d3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+// sum of squares as Vec3_c_create computes it (c:67)
+__device__ __forceinline__ double sumsq(d3 a) { return (a.x * a.x + a.y * a.y) + a.z * a.z; }
+__device__ __forceinline__ double norm(d3 a) { return sqrt(sumsq(a)); }
+__device__ __forceinline__ d3 cross(d3 a, d3 b) {
+  return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+
+struct ThreadCtx {
+  uint32_t status;
+  // lean counters (always)
+  uint32_t rays, shadow;
+  // detailed counters (count_detail only)
+  uint32_t c[RTRB_CNT_N];
+  bool detail;
+  uint32_t max_stack;
+};
+
+#define RTRB_COUNT(ctx, which) do { if ((ctx).detail) (ctx).c[which]++; } while (0)
+
+// Vec3#normalize (c:286-293)
+__device__ __forceinline__ d3 normalize(d3 a, ThreadCtx& ctx) {
+  double r = norm(a);
+  if (r == 0) ctx.status |= RTRB_ST_ZERO_VECTOR;
+  return mk(a.x / r, a.y / r, a.z / r);
+}
+// Vec3#cos (c:109-129): |cos| clamped to <= 1
+__device__ __forceinline__ double vcos(d3 a, d3 b, ThreadCtx& ctx) {
+  double ret = dot(a, b);
+  double r1 = sumsq(a), r2 = sumsq(b);
+  if (r1 == 0 || r2 == 0) ctx.status |= RTRB_ST_ZERO_VECTOR;
+  double v = sqrt(ret * ret / r1 / r2);
+  if (v > 1) v = 1;
+  return v;
+}
+__device__ __forceinline__ double rb_sqrt(double x, ThreadCtx& ctx) {
+  if (x < 0) ctx.status |= RTRB_ST_MATH_DOMAIN;
+  return sqrt(x);
+}
+__device__ __forceinline__ double rb_acos(double x, ThreadCtx& ctx) {
+  if (x < -1 || x > 1) ctx.status |= RTRB_ST_MATH_DOMAIN;
+  return acos(x);
+}
+// Float ** exponent (world.rb:76).  pow(x, 2.0) is the correctly rounded x*x.
+__device__ __forceinline__ double rb_pow(double x, double y) { return (y == 2.0) ? x * x : pow(x, y); }
+
+// ---- counter RNG: Philox4x32-10 keyed by (seed; pixel, sample, ray path, purpose) ---------------
+__device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t& c0, uint32_t& c1, uint32_t& c2,
+                                              uint32_t& c3) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+}
+__device__ __forceinline__ double res53(uint32_t a, uint32_t b) {
+  a >>= 5; b >>= 6;
+  return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
+
+// ---- object tests ------------------------------------------------------------------------------
+struct HitRec {
+  d3 p;        // intersection
+  bool dir_in; // :in / :out
+};
+
+// Sphere#intersect (sphere.rb:60-85).  d_r = |d|, dn = d / d_r are ray invariants.
+__device__ __forceinline__ bool sphere_intersect(const DevGeom& g, d3 o, d3 d, double d_r, d3 dn, HitRec& h) {
+  d3 c = mk(g.px, g.py, g.pz);
+  d3 oc = c - o;
+  double t = dot(oc, d) / (d_r * d_r);  // r2 = r*r (c:280-284)
+  d3 np = o + d * t;
+  d3 ncv = np - c;
+  double nd = norm(ncv);
+  if (!(nd <= g.radius)) return false;  // unless inner?(nearest_point)
+  double hh = sqrt(g.radius * g.radius - nd * nd);
+  d3 vec = dn * hh;
+  bool from_inner = norm(oc) <= g.radius;  // |O - C| == |C - O| bit for bit
+  h.dir_in = !from_inner;
+  h.p = h.dir_in ? (np - vec) : (np + vec);
+  if (!from_inner && t < 0) return false;
+  return true;
+}
+// Plane#intersect (plane.rb:38-51)
+__device__ __forceinline__ bool plane_intersect(const DevGeom& g, d3 o, d3 d, HitRec& h, double& den_out) {
+  d3 n = mk(g.nx, g.ny, g.nz);
+  double den = dot(n, d);
+  den_out = den;
+  if (den == 0) return false;
+  double t = dot(mk(g.px, g.py, g.pz) - o, n) / den;
+  h.p = o + d * t;
+  if (t < 0) return false;
+  h.dir_in = den < 0;
+  return true;
+}
+
+// World#lit_area (world.rb:62-69) for one light seen from `target`:
+// max(1 - sum over ALL objects of cover_area, 0), subtraction in world_objects order.
+__device__ __noinline__ double lit_area(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
+  d3 lp = mk(L.px, L.py, L.pz);
+  d3 lt = lp - target;           // ray.front of cover_area's probe ray (world_object.rb:42)
+  double lt_r = norm(lt);
+  d3 ltn = mk(lt.x / lt_r, lt.y / lt_r, lt.z / lt_r);
+  d3 tl = target - lp;
+  double total = 1;
+  for (int i = 0; i < P.n_objects; ++i) {
+    const DevGeom g = P.geom[i];
+    double cover;
+    if (g.type == RTRB_OBJ_SPHERE) {
+      RTRB_COUNT(ctx, RTRB_CNT_COV_SPH);
+      // factor = WorldObject#cover_area (world_object.rb:41-49) via Sphere#intersect
+      HitRec h;
+      int factor = 0;
+      if (sphere_intersect(g, target, lt, lt_r, ltn, h) && dot(h.p - lp, tl) > 0) factor = 1;
+      // Sphere#cover_area (sphere.rb:28-57)
+      d3 c = mk(g.px, g.py, g.pz);
+      double t = dot(c - target, lt) / (lt_r * lt_r);
+      d3 x1 = target + lt * t;
+      double r1 = L.radius * (norm(x1 - target) / lt_r);
+      double dd = norm(x1 - c);
+      if (dd >= r1 + g.radius) {
+        cover = 0;
+      } else {
+        double s1 = RTRB_PI * r1 * r1;
+        if (dd > fabs(g.radius - r1)) {
+          RTRB_COUNT(ctx, RTRB_CNT_COV_SPH_PEN);
+          double ct1 = fmin((r1 * r1 + dd * dd - g.radius * g.radius) / (2 * r1 * dd), 1.0);
+          double ct2 = fmin((g.radius * g.radius + dd * dd - r1 * r1) / (2 * g.radius * dd), 1.0);
+          double th1 = rb_acos(ct1, ctx), th2 = rb_acos(ct2, ctx);
+          double delta_s = ((th1 - sin(th1)) * r1 * r1 + (th2 - sin(th2)) * g.radius * g.radius) / 2;
+          cover = factor * delta_s / s1;
+        } else {
+          RTRB_COUNT(ctx, RTRB_CNT_COV_SPH_FULL);
+          if (r1 > g.radius) cover = factor * RTRB_PI * g.radius * g.radius / s1;
+          else cover = factor;
+        }
+      }
+    } else {
+      RTRB_COUNT(ctx, RTRB_CNT_COV_PL);
+      HitRec h; double den;
+      cover = 0;
+      if (plane_intersect(g, target, lt, h, den) && dot(h.p - lp, tl) > 0) {
+        cover = 1;
+        RTRB_COUNT(ctx, RTRB_CNT_COV_PL_ACC);
+      }
+    }
+    total -= cover;
+  }
+  return fmax(total, 0.0);
+}
+
+// get_a_random_vertical_vector (world_object.rb:105-120)
+__device__ __forceinline__ d3 a_vertical_vector(d3 n, ThreadCtx& ctx) {
+  if (norm(n) == 0) ctx.status |= RTRB_ST_ZERO_VECTOR;
+  if (n.x == 0) {
+    if (n.y == 0) return mk(1.0, 0.0, 0.0);
+    return mk(0.0, -n.z / n.y, 1.0);
+  }
+  return mk(-(n.y + n.z) / n.x, 1.0, 1.0);
+}
+
+// Texture#color (texture.rb:23-28)
+__device__ __forceinline__ d3 texture_color(const DevMat& m, double uu, double vv, ThreadCtx& ctx) {
+  double fu = (uu + m.uoff) / m.hscale, fv = (vv + m.voff) / m.vscale;
+  if (!isfinite(fu) || !isfinite(fv)) { ctx.status |= RTRB_ST_NAN_TO_INT; return mk(0, 0, 0); }
+  double mu = fmod(trunc(fu), (double)m.tex_w), mv = fmod(trunc(fv), (double)m.tex_h);
+  if (mu < 0) mu += m.tex_w;
+  if (mv < 0) mv += m.tex_h;
+  int u = (int)mu, v = (int)mv;
+  const uint8_t* p = m.tex + ((size_t)v * m.tex_w + u) * 3;
+  return mk(__ldg(p) / 256.0, __ldg(p + 1) / 256.0, __ldg(p + 2) / 256.0);
+}
+
+struct StackItem {
+  double ox, oy, oz, dx, dy, dz, ax, ay, az;
+  int32_t depth;
+  uint32_t path;
+};
+
+// RayTracer#trace_sync for one sample.  Returns the summed colour; *primary_hit gets the root ray's
+// World#intersect winner (-1 miss, -2 highlight-terminated).
+template <int MAXS>
+__device__ __forceinline__ d3 trace_sample(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
+                                           ThreadCtx& ctx, int* primary_hit) {
+  StackItem stack[MAXS];
+  int sp = 0;
+  stack[0].ox = ro.x; stack[0].oy = ro.y; stack[0].oz = ro.z;
+  stack[0].dx = rd.x; stack[0].dy = rd.y; stack[0].dz = rd.z;
+  stack[0].ax = 1.0; stack[0].ay = 1.0; stack[0].az = 1.0;
+  stack[0].depth = P.trace_depth; stack[0].path = 1u;
+  sp = 1;
+  d3 sum = mk(0.0, 0.0, 0.0);
+  bool first = true;
+  const uint32_t K = (uint32_t)(P.mc + 2);
+  *primary_hit = -1;
+
+  while (sp > 0) {
+    if ((uint32_t)sp > ctx.max_stack) ctx.max_stack = (uint32_t)sp;
+    const StackItem it = stack[--sp];
+    const bool is_first = first;
+    first = false;
+    d3 o = mk(it.ox, it.oy, it.oz), d = mk(it.dx, it.dy, it.dz), att = mk(it.ax, it.ay, it.az);
+    // rt_map :52
+    if (it.depth <= 0 || norm(att) < 0.0001) continue;
+    ctx.rays++;
+
+    // ---- World#high_lights (world.rb:83-98); occluders never block (lit_area is truthy) ----
+    unsigned long long hl_mask = 0ull;
+    int hl_n = 0;
+    for (int l = 0; l < P.n_lights; ++l) {
+      const DevLight& L = P.lights[l];
+      d3 a = mk(L.px, L.py, L.pz) - o;
+      double ct = vcos(d, a, ctx);
+      double ang = rb_acos(ct, ctx);
+      if (ang < L.hl_threshold) { hl_mask |= 1ull << l; hl_n++; }
+    }
+    if (hl_n > 0) {
+      for (int l = 0; l < P.n_lights; ++l) {
+        if (!((hl_mask >> l) & 1ull)) continue;
+        d3 c = (att * ld3(P.lights[l].color_hl)) / (double)hl_n;  // ray_tracer.rb:65
+        sum = sum + c;
+        if (sum.x > 1 || sum.y > 1 || sum.z > 1) ctx.status |= RTRB_ST_COLOR_GT_1;
+      }
+      RTRB_COUNT(ctx, RTRB_CNT_HIGHLIGHT);
+      if (is_first) *primary_hit = -2;
+      continue;
+    }
+
+    // ---- World#intersect (world.rb:37-59): linear scan, strict `<`, lowest index wins ties ----
+    const double d_r = norm(d);
+    const d3 dn = mk(d.x / d_r, d.y / d_r, d.z / d_r);
+    double best = P.max_distance;
+    int best_i = -1;
+    HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false;
+    for (int i = 0; i < P.n_objects; ++i) {
+      const DevGeom g = P.geom[i];
+      HitRec h;
+      bool ok;
+      if (g.type == RTRB_OBJ_SPHERE) {
+        RTRB_COUNT(ctx, RTRB_CNT_SPH_TEST);
+        ok = sphere_intersect(g, o, d, d_r, dn, h);
+        if (ok) RTRB_COUNT(ctx, RTRB_CNT_SPH_ACC);
+      } else {
+        RTRB_COUNT(ctx, RTRB_CNT_PL_TEST);
+        double den;
+        ok = plane_intersect(g, o, d, h, den);
+        if (ok) RTRB_COUNT(ctx, RTRB_CNT_PL_ACC);
+      }
+      if (ok) {
+        double new_dis = norm(o - h.p);  // Ray#distance (algebra.rb:10-12)
+        if (new_dis < best) { best = new_dis; best_i = i; bh = h; }
+      }
+    }
+    if (best_i < 0) continue;  // light_dead
+    if (is_first) *primary_hit = best_i;
+    RTRB_COUNT(ctx, RTRB_CNT_HITS);
+
+    const DevGeom g = P.geom[best_i];
+    const DevMat& M = P.mat[best_i];
+    // ---- intersect_parameters (sphere.rb:88-101 / plane.rb:54-67) ----
+    d3 n, delta;
+    double rate;
+    bool can_refract;
+    if (g.type == RTRB_OBJ_SPHERE) {
+      d3 c = mk(g.px, g.py, g.pz);
+      delta = ((bh.p - c) * RTRB_EPSILON) * (bh.dir_in ? 1.0 : -1.0);  // sphere.rb:84
+      n = bh.dir_in ? (bh.p - c) : (c - bh.p);
+      rate = bh.dir_in ? M.refractive_rate : 1.0 / M.refractive_rate;
+      can_refract = true;
+    } else {
+      d3 f = mk(g.nx, g.ny, g.nz);
+      double fd = dot(f, d);
+      double nfd = -fd;
+      double sgn = nfd > 0 ? 1.0 : (nfd < 0 ? -1.0 : 0.0);
+      delta = (f * RTRB_EPSILON) * sgn;  // plane.rb:50
+      n = fd > 0 ? -f : f;               // plane.rb:55
+      rate = M.refractive_rate;
+      can_refract = M.has_refraction != 0;
+    }
+    const d3 nn = normalize(n, ctx);
+    // get_reflection_by_ray_and_n (world_object.rb:121-125)
+    double cos_theta = vcos(d, -n, ctx);
+    d3 refl_dir = normalize(nn * (2 * cos_theta * d_r) + d, ctx);
+    d3 refl_org = bh.p + delta;
+    // get_refraction_by_ray_and_n (world_object.rb:127-137)
+    bool has_refr = false;
+    d3 refr_dir = mk(0, 0, 0), refr_org = mk(0, 0, 0);
+    if (can_refract) {
+      double cc = vcos(d, n, ctx);
+      double sin_i = rb_sqrt(1 - cc * cc, ctx);
+      double sin_r = sin_i / rate;
+      if (!(sin_r >= 1)) {
+        if (sin_r < -1 || sin_r > 1) ctx.status |= RTRB_ST_MATH_DOMAIN;
+        double r = asin(sin_r);
+        refr_dir = nn * (-cos(r)) + normalize(refl_dir + d, ctx) * sin_r;
+        refr_org = bh.p - nn * RTRB_EPSILON;
+        has_refr = true;
+      }
+    }
+    // push children: reflection first, refraction second (popped first)  ray_tracer.rb:87-121
+    if (sp + 2 + P.mc > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; continue; }
+    {
+      StackItem& s = stack[sp++];
+      d3 a2 = att * ld3(M.refl);
+      s.ox = refl_org.x; s.oy = refl_org.y; s.oz = refl_org.z;
+      s.dx = refl_dir.x; s.dy = refl_dir.y; s.dz = refl_dir.z;
+      s.ax = a2.x; s.ay = a2.y; s.az = a2.z;
+      s.depth = it.depth - 1; s.path = it.path * K + 0u;
+    }
+    if (has_refr) {
+      RTRB_COUNT(ctx, RTRB_CNT_REFR);
+      StackItem& s = stack[sp++];
+      d3 a2 = att * ld3(M.refr);
+      s.ox = refr_org.x; s.oy = refr_org.y; s.oz = refr_org.z;
+      s.dx = refr_dir.x; s.dy = refr_dir.y; s.dz = refr_dir.z;
+      s.ax = a2.x; s.ay = a2.y; s.az = a2.z;
+      s.depth = it.depth - 1; s.path = it.path * K + 1u;
+    }
+
+    // ---- World#local_lights (world.rb:72-80) fused with WorldObject#local_lighting (:51-74) ----
+    const d3 shade_from = bh.p + delta;
+    d3 contrib = mk(0.0, 0.0, 0.0);
+    int n_lit = 0;
+    for (int l = 0; l < P.n_lights; ++l) {
+      const DevLight& L = P.lights[l];
+      ctx.shadow++;
+      double area = lit_area(P, shade_from, L, ctx);
+      if (area > 0) {
+        d3 lc = ld3(L.color) * (rb_pow(area, P.soft_shadow_exponent) / (double)P.n_lights);
+        d3 lv = normalize(mk(L.px, L.py, L.pz) - bh.p, ctx);  // shading point is WITHOUT delta (:152)
+        double ldn = dot(lv, nn);
+        if (ldn > 1) ldn = 1.0; else if (ldn < 0) ldn = 0.0;
+        contrib = contrib + lc * ldn;
+        n_lit++;
+      }
+    }
+    if (n_lit == 0) {
+      // WorldObject#path_tracing (world_object.rb:76-90): mc rays, no local/ambient colour
+      if (P.mc > 0) {
+        d3 att_pt = ld3(M.diffuse) / (double)P.mc;
+        d3 leftv = normalize(a_vertical_vector(n, ctx), ctx);
+        d3 upv = cross(nn, leftv);
+        for (int m = 0; m < P.mc; ++m) {
+          uint32_t child = it.path * K + (uint32_t)(2 + m);
+          uint32_t c0 = pixel, c1 = sample, c2 = child, c3 = 1u;
+          philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
+          double theta = res53(c0, c1) * RTRB_PI / 2, phi = res53(c2, c3) * RTRB_PI * 2;
+          d3 dir = nn * sin(theta) + (leftv * cos(phi) + upv * sin(phi)) * cos(theta);
+          RTRB_COUNT(ctx, RTRB_CNT_MC);
+          StackItem& s = stack[sp++];
+          d3 a2 = att * att_pt;
+          s.ox = shade_from.x; s.oy = shade_from.y; s.oz = shade_from.z;
+          s.dx = dir.x; s.dy = dir.y; s.dz = dir.z;
+          s.ax = a2.x; s.ay = a2.y; s.az = a2.z;
+          s.depth = it.depth - 1; s.path = child;
+        }
+      }
+    } else {
+      RTRB_COUNT(ctx, RTRB_CNT_LOCAL);
+      if (ctx.detail) ctx.c[RTRB_CNT_LIT] += n_lit;
+      contrib = contrib / (double)n_lit;  // world_object.rb:66-68
+      d3 filter = mk(1.0, 1.0, 1.0);
+      if (M.tex != nullptr) {
+        double u, v;
+        if (g.type == RTRB_OBJ_SPHERE) {  // Sphere#get_uv (sphere.rb:111-120)
+          d3 vec = bh.p - mk(g.px, g.py, g.pz);
+          double x = dot(vec, ld3(M.e0)) / g.radius;
+          double y = dot(vec, ld3(M.e1)) / g.radius;
+          double z = dot(vec, ld3(M.e2)) / g.radius;
+          double mm = rb_sqrt(x * x + y * y + z * z + 2 * x + 1, ctx);
+          u = (y / mm + 1) / 2;
+          v = (-z / mm + 1) / 2;
+        } else {  // Plane#get_uv (plane.rb:81-85)
+          d3 rel = bh.p - mk(g.px, g.py, g.pz);
+          u = dot(rel, ld3(M.e0)) / M.u_unit;
+          v = dot(rel, ld3(M.e1)) / M.v_unit;
+        }
+        RTRB_COUNT(ctx, RTRB_CNT_TEXEL);
+        filter = texture_color(M, u, v, ctx) * filter;
+      }
+      d3 local = ((contrib * ld3(M.diffuse)) * filter) + ld3(M.ambient);
+      d3 c = att * local;  // ray_tracer.rb:152
+      sum = sum + c;
+      if (sum.x > 1 || sum.y > 1 || sum.z > 1) ctx.status |= RTRB_ST_COLOR_GT_1;
+    }
+  }
+  return sum;
+}
+
+// Camera#lens_func (camera.rb:129-151) for pixel (x, y) and aperture angle theta.
+__device__ __forceinline__ void lens_ray(const FrameParams& P, int x, int y, double theta, d3& ro, d3& rd) {
+  d3 pos = ld3(P.pos), left = ld3(P.left), upn = ld3(P.up_n), front = ld3(P.front);
+  double sx = 2.0 * ((double)x / P.width - 0.5) * P.retina_width;
+  double sy = 2 * ((double)y / P.height - 0.5) * P.retina_height;
+  d3 retina_position = (ld3(P.retina_center) + left * sx) + upn * sy;
+  d3 rand_vector = (ld3(P.left_n) * cos(theta) + upn * sin(theta)) * P.aperture_radius;
+  d3 aperture = pos + rand_vector;
+  d3 rf = pos - retina_position;  // ray retina -> lens centre
+  double t = dot(ld3(P.focal_point) - retina_position, front) / dot(front, rf);  // intersect_plane :123-127
+  d3 target = retina_position + rf * t;
+  ro = aperture;
+  rd = target - aperture;
+}
+
+// Decodes work item -> (tile slot k, in-tile q, x, y); returns false when the pixel is outside the window.
+__device__ __forceinline__ bool decode_pixel(const FrameParams& P, uint32_t slot, int& x, int& y) {
+  uint32_t k = slot / RTRB_SUPER_PIXELS, q = slot % RTRB_SUPER_PIXELS;
+  int tile = P.tiles[k];
+  int qx, qy;
+  rtrb_morton_decode(q, &qx, &qy);
+  x = (tile % P.stx_count) * RTRB_SUPER + qx;
+  y = (tile / P.stx_count) * RTRB_SUPER + qy;
+  return x >= P.x0 && x < P.x1 && y >= P.y0 && y < P.y1;
+}
+
+__device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, int x, int y, bool active) {
+  // warp-aggregate the two lean counters, then one atomic per warp
+  const unsigned full = 0xffffffffu;
+  uint32_t rays = ctx.rays, shadow = ctx.shadow, ms = ctx.max_stack;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rays += __shfl_xor_sync(full, rays, o);
+    shadow += __shfl_xor_sync(full, shadow, o);
+    ms = max(ms, __shfl_xor_sync(full, ms, o));
+  }
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) {
+    if (rays) atomicAdd(&P.counters[RTRB_CNT_RAYS], (unsigned long long)rays);
+    if (shadow) atomicAdd(&P.counters[RTRB_CNT_SHADOW], (unsigned long long)shadow);
+    atomicMax(&P.status[1], ms);
+  }
+  if (ctx.detail) {
+    for (int i = 0; i < RTRB_CNT_N; ++i) {
+      if (i == RTRB_CNT_RAYS || i == RTRB_CNT_SHADOW) continue;
+      uint32_t v = ctx.c[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+      if (lane == 0 && v) atomicAdd(&P.counters[i], (unsigned long long)v);
+    }
+  }
+  if (active && ctx.status) {
+    atomicOr(&P.status[0], ctx.status);
+    atomicMin(P.first_bad, (unsigned long long)x * (unsigned long long)P.height + (unsigned long long)y);
+  }
+}
+
+__device__ __forceinline__ void init_ctx(ThreadCtx& ctx, bool detail) {
+  ctx.status = 0; ctx.rays = 0; ctx.shadow = 0; ctx.max_stack = 0; ctx.detail = detail;
+#pragma unroll
+  for (int i = 0; i < RTRB_CNT_N; ++i) ctx.c[i] = 0;
+}
+
+// One thread per (pixel, sample j < pre_sample_times): the first loop of render_at (camera.rb:73-78).
+template <int MAXS, bool DETAIL>
+__device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
+  const uint32_t S = (uint32_t)P.pre;
+  const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long total = (unsigned long long)P.n_tiles * RTRB_SUPER_PIXELS * S;
+  ThreadCtx ctx;
+  init_ctx(ctx, DETAIL);
+  int x = 0, y = 0;
+  bool active = false;
+  if (w < total) {
+    const uint32_t slot = (uint32_t)(w / S), j = (uint32_t)(w % S);
+    active = decode_pixel(P, slot, x, y);
+    if (active) {
+      const uint32_t pixel = (uint32_t)y * (uint32_t)P.width + (uint32_t)x;
+      uint32_t c0 = pixel, c1 = j, c2 = 0u, c3 = 0u;
+      philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
+      double theta = res53(c0, c1);  // Random.rand, camera.rb:135
+      d3 ro, rd;
+      lens_ray(P, x, y, theta, ro, rd);
+      int ph;
+      d3 col = trace_sample<MAXS>(P, ro, rd, pixel, j, ctx, &ph);
+      RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
+      double* out = P.samples + w * 3ull;
+      out[0] = col.x; out[1] = col.y; out[2] = col.z;
+      if (j == 0 && P.hit) P.hit[(size_t)y * P.width + x] = ph;
+    }
+  }
+  flush_ctx(P, ctx, x, y, active);
+}
+
+// Extra samples j in [pre, max) of the pixels that failed the variance test (camera.rb:88-93);
+// persistent grid-stride loop because the pixel count is only known on the device.
+template <int MAXS, bool DETAIL>
+__device__ __forceinline__ void trace_extra_body(const FrameParams& P) {
+  const uint32_t E = (uint32_t)(P.max_samples - P.pre);
+  const unsigned long long total = (unsigned long long)(*P.extra_count) * E;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  ThreadCtx ctx;
+  init_ctx(ctx, DETAIL);
+  int x = 0, y = 0;
+  bool any = false;
+  for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+    const uint32_t e = (uint32_t)(w / E), j = (uint32_t)P.pre + (uint32_t)(w % E);
+    const uint32_t slot = P.extra_list[e];
+    if (!decode_pixel(P, slot, x, y)) continue;
+    any = true;
+    const uint32_t pixel = (uint32_t)y * (uint32_t)P.width + (uint32_t)x;
+    uint32_t c0 = pixel, c1 = j, c2 = 0u, c3 = 0u;
+    philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
+    double theta = res53(c0, c1);
+    d3 ro, rd;
+    lens_ray(P, x, y, theta, ro, rd);
+    int ph;
+    d3 col = trace_sample<MAXS>(P, ro, rd, pixel, j, ctx, &ph);
+    RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
+    double* out = P.extra_samples + w * 3ull;
+    out[0] = col.x; out[1] = col.y; out[2] = col.z;
+  }
+  flush_ctx(P, ctx, x, y, any);
+}
+
+}  // namespace rtrb

@@ -1,0 +1,112 @@
+// rtrb_types.h — device-side data layout shared by the host API (rtrb_api.cu) and the kernels.
+//
+// Scene data is baked ONCE at rtrb_renderer_create into flat arrays (DESIGN.md "Data layout"):
+//   geom[]  : one 64-byte record per world object, in world.yml order, read by every lane of a warp
+//             at the same index (broadcast) while scanning objects (World#intersect world.rb:44-57,
+//             World#lit_area world.rb:64-67);
+//   mat[]   : one record per object, read only for the object a ray actually hit;
+//   lights[]: one record per light;
+//   textures: 8-bit RGB rows, texel = v8/256.0 (texture.rb:19).
+#pragma once
+#include <stdint.h>
+
+#define RTRB_MAX_LIGHTS 64
+#define RTRB_SUPER 32                 // super-tile edge in pixels (tile partition unit across GPUs)
+#define RTRB_SUPER_PIXELS (RTRB_SUPER * RTRB_SUPER)
+
+struct DevGeom {      // 64 B
+  double px, py, pz;  // sphere centre / plane point
+  double radius;      // sphere radius (0 for planes)
+  double nx, ny, nz;  // plane front (unnormalised, as the reference keeps it)
+  int32_t type;       // RTRB_OBJ_*
+  int32_t pad;
+};
+
+struct DevMat {
+  double diffuse[3], refl[3], refr[3], ambient[3];
+  double refractive_rate;
+  // texture frame: sphere (sphere.rb:111-120): e0 = greenwich^, e1 = ninety_degree_east^, e2 = north^
+  //                plane  (plane.rb:81-85):    e0 = left^ (normalised twice, as upstream), e1 = up^
+  double e0[3], e1[3], e2[3];
+  double u_unit, v_unit;
+  double hscale, vscale, uoff, voff;
+  const uint8_t* tex;   // device pointer to rows of RGB8, or nullptr
+  int32_t tex_w, tex_h;
+  int32_t has_refraction;
+  int32_t pad;
+};
+
+struct DevLight {
+  double px, py, pz;
+  double color[3];
+  double color_hl[3];   // color * high_light_rate (world.rb:94)
+  double radius;
+  double hl_threshold;  // high_light_angle / 180.0 * PI (world.rb:92)
+};
+
+// Per-frame constants: thin-lens camera baked on the host in the reference's evaluation order
+// (camera.rb:129-151) + sampling + tiling.  Passed by value as a __grid_constant__ kernel parameter.
+struct FrameParams {
+  // camera
+  double pos[3];
+  double front[3];          // as given (focal-plane normal, camera.rb:144)
+  double left[3];           // normalize(up x front)            camera.rb:130
+  double left_n[3];         // normalize(left)                  camera.rb:136
+  double up_n[3];           // normalize(up)
+  double retina_center[3];  // pos - front^ * image_distance    camera.rb:131
+  double focal_point[3];    // pos + front^ * object_distance   camera.rb:143
+  double retina_width, retina_height, aperture_radius;
+  double variant_threshold;
+  int32_t width, height;
+  int32_t pre, max_samples;
+  int32_t trace_depth, mc;
+  // world
+  double max_distance, soft_shadow_exponent;
+  int32_t n_objects, n_lights;
+  const DevGeom* geom;
+  const DevMat* mat;
+  const DevLight* lights;
+  // rng
+  uint32_t key0, key1;
+  // work domain
+  int32_t x0, y0, x1, y1;      // window
+  int32_t n_tiles;             // super-tiles assigned to this renderer for this frame
+  int32_t stx_count;           // super-tiles per row of the full image
+  const int32_t* tiles;        // [n_tiles] global super-tile ids (sty * stx_count + stx)
+  // outputs / scratch
+  double* samples;             // [n_tiles * 1024 * S][3] per-sample colours of the current pass
+  double* rgb;                 // [H][W][3] or nullptr
+  int32_t* hit;                // [H][W] or nullptr
+  uint8_t* rgba;               // [H][W][4] (may be a peer mapping)
+  unsigned long long* counters;// RTRB_CNT_* u64 counters
+  uint32_t* status;            // [0] status bits, [1] max stack
+  unsigned long long* first_bad;// min over flagged pixels of x*H + y
+  // adaptive pass
+  uint32_t* extra_count;       // number of pixels taking the extra-sample branch
+  uint32_t* extra_list;        // [n_tiles*1024] pixel slots (tile k * 1024 + q)
+  double* extra_samples;       // [extra][max-pre][3]
+  int32_t count_detail;
+  int32_t pad;
+};
+
+enum {
+  RTRB_CNT_SAMPLES = 0, RTRB_CNT_RAYS, RTRB_CNT_SHADOW, RTRB_CNT_HIGHLIGHT, RTRB_CNT_HITS, RTRB_CNT_LOCAL,
+  RTRB_CNT_LIT, RTRB_CNT_MC, RTRB_CNT_REFR, RTRB_CNT_TEXEL, RTRB_CNT_SPH_TEST, RTRB_CNT_SPH_ACC,
+  RTRB_CNT_PL_TEST, RTRB_CNT_PL_ACC, RTRB_CNT_COV_SPH, RTRB_CNT_COV_SPH_FULL, RTRB_CNT_COV_SPH_PEN,
+  RTRB_CNT_COV_PL, RTRB_CNT_COV_PL_ACC, RTRB_CNT_ADAPTIVE, RTRB_CNT_EXACT, RTRB_CNT_N
+};
+
+// Morton decode of the 10-bit in-super-tile index q: even bits -> x, odd bits -> y, so that 32
+// consecutive q cover an 8x4 pixel block (warp-coherent tile ordering).
+__host__ __device__ inline void rtrb_morton_decode(uint32_t q, int* qx, int* qy) {
+  uint32_t x = q & 0x155u, y = (q >> 1) & 0x155u;
+  x = (x | (x >> 1)) & 0x133u; x = (x | (x >> 2)) & 0x10Fu; x = (x | (x >> 4)) & 0x1Fu;
+  y = (y | (y >> 1)) & 0x133u; y = (y | (y >> 2)) & 0x10Fu; y = (y | (y >> 4)) & 0x1Fu;
+  *qx = (int)x; *qy = (int)y;
+}
+__host__ __device__ inline uint32_t rtrb_morton_encode(int qx, int qy) {
+  uint32_t x = (uint32_t)qx & 0x1Fu, y = (uint32_t)qy & 0x1Fu;
+  x = (x | (x << 4)) & 0x10Fu; x = (x | (x << 2)) & 0x133u; x = (x | (x << 1)) & 0x155u;
+  y = (y | (y << 4)) & 0x10Fu; y = (y | (y << 2)) & 0x133u; y = (y | (y << 1)) & 0x155u;
+  return x | (y << 1);
+}

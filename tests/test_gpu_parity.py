@@ -1,0 +1,132 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, raytracing_rb_b200/csrc) against the
+CPU oracle on the same seeded inputs.  Tiers (BASELINE.json north_star):
+  * deterministic configs: 8-bit output within +-1 LSB on >= 99.9% of pixels, max abs diff stated;
+  * primary hit ids bit-exact;
+  * ray / shadow-query counters exactly equal.
+STRICT mode is additionally held to a much tighter bar (float RGB within 1e-12)."""
+import numpy as np
+import pytest
+
+from helpers_rtrb import compare_u8, load_scene
+from raytracing_rb_b200 import PREC_FAST64, PREC_STRICT, make_opts
+
+pytestmark = pytest.mark.gpu
+
+COUNTERS = ("samples", "rays", "shadow_queries", "highlight_hits", "hits", "local_shaded", "lit_lights", "mc_rays",
+            "refractions", "texel_fetches", "sphere_tests", "sphere_accepts", "plane_tests", "plane_accepts",
+            "cover_sphere", "cover_sphere_full", "cover_sphere_penumbra", "cover_plane", "cover_plane_accepts",
+            "adaptive_pixels")
+
+
+def run_both(oracle_mod, config_id, precision, seed=1, **kw):
+    world, cam = load_scene(config_id, **kw)
+    ref = oracle_mod.OracleScene(world.to_scene_desc()).render(cam.camera_desc(), make_opts(seed=seed))
+    got = cam.render_frame(seed=seed, precision=precision, count_detail=True)
+    return ref, got
+
+
+def check(ref, got, strict):
+    frac, maxdiff, ndiff = compare_u8(got.rgba, ref.rgba)
+    print("within+-1LSB=%.6f max_abs_diff=%d differing_px=%d" % (frac, maxdiff, ndiff))
+    assert frac >= 0.999
+    assert np.array_equal(got.hit, ref.hit), "primary hit ids must be bit-exact"
+    for k in COUNTERS:
+        if strict or k in ("samples", "rays", "shadow_queries", "hits", "highlight_hits", "local_shaded",
+                           "lit_lights", "mc_rays", "refractions", "texel_fetches", "adaptive_pixels"):
+            assert got.stats[k] == ref.stats[k], k
+    assert got.stats["status"] == ref.stats["status"]
+    if strict:
+        assert np.abs(got.rgb - ref.rgb).max() <= 1e-12
+        assert maxdiff <= 1
+    assert (got.rgba[..., 3] == 255).all()
+
+
+@pytest.mark.parametrize("precision", [PREC_STRICT, PREC_FAST64])
+def test_config1_default_scene(oracle_mod, precision):
+    ref, got = run_both(oracle_mod, 1, precision)
+    check(ref, got, precision == PREC_STRICT)
+    assert got.stats["max_stack"] == ref.stats["max_stack"] or precision != PREC_STRICT
+
+
+@pytest.mark.parametrize("precision", [PREC_STRICT, PREC_FAST64])
+def test_config2_full_size_deterministic(oracle_mod, precision):
+    ref, got = run_both(oracle_mod, 2, precision)  # 1920x1080
+    check(ref, got, precision == PREC_STRICT)
+
+
+@pytest.mark.parametrize("precision", [PREC_STRICT, PREC_FAST64])
+def test_config3_recursion_texture(oracle_mod, precision):
+    ref, got = run_both(oracle_mod, 3, precision, width=480, height=270)
+    check(ref, got, precision == PREC_STRICT)
+
+
+@pytest.mark.parametrize("precision", [PREC_STRICT, PREC_FAST64])
+def test_config4_soft_shadow_mc(oracle_mod, precision):
+    ref, got = run_both(oracle_mod, 4, precision, width=240, height=135)
+    check(ref, got, precision == PREC_STRICT)
+
+
+@pytest.mark.parametrize("precision", [PREC_STRICT, PREC_FAST64])
+def test_config5_many_spheres(oracle_mod, precision):
+    ref, got = run_both(oracle_mod, 5, precision, width=96, height=54, spp=2)
+    check(ref, got, precision == PREC_STRICT)
+
+
+def test_window_and_tiles_compose(oracle_mod):
+    """A column strip (render_fork's child_work, camera.rb:53-65) and an interleaved tile subset
+    reproduce exactly the same pixels as the full frame (counter RNG keyed by pixel)."""
+    world, cam = load_scene(3, width=200, height=120)
+    full = cam.render_frame(seed=7)
+    strip = cam.render_frame(seed=7, window=(50, 0, 100, 120))
+    assert np.array_equal(strip.rgba[:, 50:100], full.rgba[:, 50:100])
+    assert (strip.hit[:, :50] == -3).all() and (strip.hit[:, 100:] == -3).all()
+    r = cam.renderer()
+    c = cam.camera_desc()
+    acc = np.zeros_like(full.rgba)
+    rays = 0
+    for rank in range(3):
+        f = r.render(c, make_opts(seed=7, tile_rank=rank, tile_world=3))
+        mask = f.hit != -3
+        acc[mask] = f.rgba[mask]
+        rays += f.stats["rays"]
+    assert np.array_equal(acc, full.rgba)
+    assert rays == full.stats["rays"]
+
+
+def test_render_at_matches_frame(oracle_mod):
+    world, cam = load_scene(1)
+    full = cam.render_frame(seed=1)
+    for (x, y) in ((0, 0), (96, 54), (191, 107), (130, 60)):
+        item = cam.render_at(x, y, seed=1)
+        assert item["position"] == [x, cam.height - 1 - y]
+        assert item["color"] == [float(v) for v in full.rgb[y, x]]
+
+
+def test_status_word_color_greater_than_one(oracle_mod):
+    from raytracing_rb_b200 import Camera, World, scenes, _abi
+    g = scenes.ground()
+    g["properties"]["ambient"] = [0.9, 0.9, 0.9]
+    w = World({"max_distance": 10000, "soft_shadow_exponent": 2, "lights": [scenes.light([5, -4, 4], 0.0)],
+               "world_objects": [g]})
+    _, cdoc = scenes.build(2, width=64, height=36)
+    cam = Camera(w, cdoc)
+    ref = oracle_mod.OracleScene(w.to_scene_desc()).render(cam.camera_desc())
+    got = cam.render_frame()
+    assert got.raised and got.stats["status"] & _abi.ST_COLOR_GT_1
+    assert (got.stats["first_bad_x"], got.stats["first_bad_y"]) == (ref.stats["first_bad_x"], ref.stats["first_bad_y"])
+    assert np.array_equal(got.rgba, ref.rgba)
+    with pytest.raises(RuntimeError, match="color greater than 1"):
+        cam.render_cuda(None)
+
+
+def test_device_rejects_what_it_cannot_do(oracle_mod):
+    from raytracing_rb_b200 import _abi
+    from raytracing_rb_b200._lib import RtrbError
+    world, cam = load_scene(1)
+    with pytest.raises(RtrbError):
+        cam.renderer().render(cam.camera_desc(), make_opts(rng_mode=_abi.RNG_MT))
+    c = cam.camera_desc()
+    c.trace_depth = 100
+    c.monte_carlo_diffusion_times = 4
+    with pytest.raises(RtrbError):
+        cam.renderer().render(c, make_opts())
