@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s and frames/s of the raytracing_rb hot path on 1/2/4/8 B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+A "step" is one frame of the workload BASELINE.json's metric is quoted on (configs[1]: 1920x1080,
+ground plane + 16 spheres, hard shadows, 1 spp, no recursion).  Metric: Mrays/s where rays =
+traced rays (work-stack items passing the cut at ray_tracer.rb:52) + shadow queries (lit_area calls
+from local_lights, world.rb:75), SURVEY.md 8d.
+
+For N > 1 (torchrun, one rank per GPU) the frame's 32x32-pixel super-tiles are dealt round-robin
+to the ranks and every rank's resolve kernel writes its pixels straight into rank 0's framebuffer
+through a CUDA-IPC peer mapping over NVLink: no collective on the data path (strong scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# SURVEY.md 8d algorithmic FLOP constants (add/mul = 1, FMA = 2, div/sqrt = 1, transcendental = 1)
+FLOP = dict(ray=7, sphere_reject=20, sphere_accept=44, plane_reject=14, plane_accept=29, hit=82 + 2,
+            lambert_per_light=24, lambert_base=15, uv=34, shadow=10, cover_sphere_none=24, cover_sphere_full=56,
+            cover_sphere_pen=83 + 4, cover_plane_reject=14, cover_plane_accept=37, primary=60 + 2)
+
+
+def algorithmic_flops(s):
+    return (s["rays"] * FLOP["ray"]
+            + (s["sphere_tests"] - s["sphere_accepts"]) * FLOP["sphere_reject"] + s["sphere_accepts"] * FLOP["sphere_accept"]
+            + (s["plane_tests"] - s["plane_accepts"]) * FLOP["plane_reject"] + s["plane_accepts"] * FLOP["plane_accept"]
+            + s["hits"] * FLOP["hit"] + s["lit_lights"] * FLOP["lambert_per_light"] + s["local_shaded"] * FLOP["lambert_base"]
+            + s["texel_fetches"] * FLOP["uv"] + s["shadow_queries"] * FLOP["shadow"]
+            + (s["cover_sphere"] - s["cover_sphere_full"] - s["cover_sphere_penumbra"]) * FLOP["cover_sphere_none"]
+            + s["cover_sphere_full"] * FLOP["cover_sphere_full"] + s["cover_sphere_penumbra"] * FLOP["cover_sphere_pen"]
+            + (s["cover_plane"] - s["cover_plane_accepts"]) * FLOP["cover_plane_reject"]
+            + s["cover_plane_accepts"] * FLOP["cover_plane_accept"] + s["samples"] * FLOP["primary"])
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode()
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def workload(config_id, small):
+    from raytracing_rb_b200 import Camera, World, scenes
+    kw = {}
+    if small:
+        kw = dict(width=480, height=270)
+    wdoc, cdoc = scenes.build(config_id, **kw)
+    return World(wdoc), cdoc, scenes.NAMES[config_id]
+
+
+def run_reference(args, rank, world_size):
+    """The reference's own CPU implementation of the path: no Ruby interpreter exists in this image
+    (probed below), so this is the FP64 C++ restatement (oracle/, `kind: port`) run as column strips
+    over every host core exactly like render_fork (camera.rb:53-65)."""
+    if rank != 0:
+        return
+    from raytracing_rb_b200 import Camera, make_opts
+    from oracle import oracle
+    world, cdoc, name = workload(args.config, args.small)
+    cd = Camera(world, cdoc).camera_desc()
+    cores = os.cpu_count() or 1
+    sc = oracle.OracleScene(world.to_scene_desc())
+    # bounded sample: a centred window sized so one step stays within seconds on the host cores
+    frac = args.cpu_fraction
+    W, H = cd.width, cd.height
+    ww = max(cores, int(W * frac))
+    win = ((W - ww) // 2, 0, (W - ww) // 2 + ww, H)
+    opts = make_opts(seed=1, window=win)
+    for _ in range(args.warmup):
+        sc.render(cd, opts, threads=cores, want_rgb=False, want_hit=False)
+    t0 = time.perf_counter()
+    rays = 0
+    for _ in range(args.steps):
+        f = sc.render(cd, opts, threads=cores, want_rgb=False, want_hit=False)
+        rays += f.stats["rays"] + f.stats["shadow_queries"]
+    dt = time.perf_counter() - t0
+    value = rays / dt / 1e6
+    sample = "window x in [%d,%d) of %dx%d (%.0f%% of the frame) per step, %d column strips" % (
+        win[0], win[2], W, H, 100.0 * ww / W, cores)
+    ruby = subprocess.call("command -v ruby", shell=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 0
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "host": "CPU only", "ruby_present": ruby},
+        "frames_per_s_equiv": args.steps / dt * (ww / W),
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, local_rank, world_size):
+    import torch
+    from raytracing_rb_b200 import (Camera, Renderer, _abi, ipc_open, make_opts, measure_fma_peak, PREC_FAST64,
+                                    PREC_STRICT)
+    from raytracing_rb_b200._lib import lib, check
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    precision = PREC_STRICT if args.precision == "strict" else PREC_FAST64
+    world, cdoc, name = workload(args.config, args.small)
+    cd = Camera(world, cdoc).camera_desc()
+    W, H = cd.width, cd.height
+    r = Renderer(world.to_scene_desc(), local_rank)
+
+    # ---- where the pixels go: rank 0's framebuffer (peer mapping for the other ranks) ----
+    peer_ptr = None
+    if world_size > 1:
+        hbuf = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            hbuf.copy_(torch.frombuffer(bytearray(r.framebuffer_ipc_export(W, H)), dtype=torch.uint8))
+        dist.broadcast(hbuf, 0)
+        if rank != 0:
+            peer_ptr = ipc_open(local_rank, bytes(hbuf.cpu().numpy().tobytes()))
+    stream = torch.cuda.current_stream()
+
+    def opts(detail=False):
+        return make_opts(seed=1, precision=precision, tile_rank=rank, tile_world=world_size, count_detail=detail,
+                         stream=stream.cuda_stream, rgba_device_out=peer_ptr)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- untimed: per-frame work of this rank (counters) and the FMA issue peaks ----
+    st_detail, _ = r.render_device(cd, opts(True))
+    flops_frame = algorithmic_flops(st_detail)
+    rays_frame = st_detail["rays"] + st_detail["shadow_queries"]
+    peak64 = measure_fma_peak(local_rank, True) if rank == 0 else 0.0
+    peak32 = measure_fma_peak(local_rank, False) if rank == 0 else 0.0
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    for _ in range(max(args.warmup, 3)):
+        r.render_device(cd, opts(), want_stats=False)
+    barrier()
+
+    # ---- timed: EXACTLY K steps, CUDA events on the launch stream, L2 flushed between steps ----
+    launches0 = lib().rtrb_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    o = opts()
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record(stream)
+        r.render_device(cd, o, want_stats=False)
+        ev[k][1].record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = lib().rtrb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
+    rays_t = torch.tensor([float(rays_frame), float(flops_frame)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # a frame is done when its slowest rank is
+        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
+    total_ms = float(step_ms.sum().item())
+    rays_total, flops_total = float(rays_t[0].item()), float(rays_t[1].item())
+    value = rays_total * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- dominant kernel alone (trace over the pre samples): library-side CUDA events ----
+    tr = []
+    for _ in range(min(args.steps, 20)):
+        flush.zero_()
+        st, _ = r.render_device(cd, opts())
+        tr.append(st["trace_ms"])
+    trace_ms = float(np.mean(tr))
+
+    # ---- e2e: the public frame call with HOST buffers (pinned), copies inside the timed region ----
+    host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+    host_np = host.numpy()
+    cam_bytes = C.sizeof(_abi.CameraDesc) + C.sizeof(_abi.RenderOpts)
+
+    def e2e_step():
+        if world_size == 1:
+            r.render(cd, make_opts(seed=1, precision=precision), want_rgb=False, want_hit=False, out_rgba=host_np)
+        else:
+            r.render_device(cd, opts(), want_stats=False)
+            barrier()  # all ranks' tiles have landed in rank 0's framebuffer
+            if rank == 0:
+                check(lib().rtrb_download(r.handle, host_np.ctypes.data, None, None))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = rays_total * args.steps / float(e2e_dt.item()) / 1e6
+
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "precision_mode": args.precision, "rays_per_frame": rays_total,
+                       "l2": "flushed between timed steps (256 MiB write)", "tiles": "32x32 px round-robin over ranks",
+                       "rng": "philox4x32-10 counter, seed 1"},
+            "frames_per_s": args.steps / (total_ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": cam_bytes,
+                    "d2h_bytes_per_step": W * H * 4, "frames_per_s": args.steps / float(e2e_dt.item())},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "wall_s_timed_region": wall,
+        }
+        if world_size == 1:
+            achieved = flops_frame / (trace_ms * 1e-3) / 1e12
+            line["roofline"] = {
+                "bound": "fp64", "kernel": "trace_pre_*_kernel", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
+                "frac": achieved / peak64 if peak64 else None, "traffic": None,
+                "peak_source": "measured in this job: dependent-free DFMA microbenchmark (rtrb_measure_fma_peak)",
+                "peak_fp32": peak32, "algorithmic_flops_per_launch": flops_frame, "kernel_ms": trace_ms,
+                "note": "FP-issue bound path (SURVEY.md 8d): HBM traffic is the 4 B/pixel framebuffer write only",
+            }
+            line["cpu_baseline"] = cpu_baseline(args, world, cd, name)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, world, cd, name):
+    """The oracle (kind 'port') on the GPU box's host cores, bounded sample of the same workload."""
+    from raytracing_rb_b200 import make_opts
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    sc = oracle.OracleScene(world.to_scene_desc())
+    W, H = cd.width, cd.height
+    ww = max(cores, int(W * args.cpu_fraction))
+    win = ((W - ww) // 2, 0, (W - ww) // 2 + ww, H)
+    o = make_opts(seed=1, window=win)
+    sc.render(cd, o, threads=cores, want_rgb=False, want_hit=False)
+    t0 = time.perf_counter()
+    n, rays = 0, 0
+    while True:
+        f = sc.render(cd, o, threads=cores, want_rgb=False, want_hit=False)
+        rays += f.stats["rays"] + f.stats["shadow_queries"]
+        n += 1
+        if time.perf_counter() - t0 > 10.0 or n >= 50:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+            "sample": "%d passes over window x in [%d,%d) of %dx%d, %d column strips (render_fork shape)" % (
+                n, win[0], win[2], W, H, cores)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--precision", default="fast64", choices=["fast64", "strict"])
+    ap.add_argument("--small", action="store_true", help="480x270 variant for quick checks (not a bench value)")
+    ap.add_argument("--cpu-fraction", type=float, default=1.0, help="fraction of the frame width the CPU legs render")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world_size)
+    else:
+        run_ours(args, rank, local_rank, world_size)
+
+
+if __name__ == "__main__":
+    main()

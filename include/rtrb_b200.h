@@ -162,7 +162,7 @@ typedef struct rtrb_stats {
   int32_t first_bad_x, first_bad_y; /* lowest (y*W+x) pixel that set a status bit, -1 if none */
   uint32_t max_stack;         /* deepest work stack seen */
   float device_ms;            /* CUDA-event time of the frame's kernels on the launch stream */
-  float reserved1;
+  float trace_ms;             /* CUDA-event time of the dominant kernel alone (trace over the pre samples) */
 } rtrb_stats;
 
 typedef struct rtrb_renderer rtrb_renderer; /* opaque: scene SoA + scratch + framebuffers on ONE device */

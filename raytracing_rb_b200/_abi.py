@@ -88,7 +88,7 @@ class Stats(C.Structure):
         ("adaptive_pixels", C.c_uint64), ("exact_tests", C.c_uint64),
         ("reserved", C.c_uint64 * 4),
         ("status", C.c_uint32), ("first_bad_x", C.c_int32), ("first_bad_y", C.c_int32),
-        ("max_stack", C.c_uint32), ("device_ms", C.c_float), ("reserved1", C.c_float),
+        ("max_stack", C.c_uint32), ("device_ms", C.c_float), ("trace_ms", C.c_float),
     ]
 
     COUNTER_FIELDS = (
@@ -101,5 +101,5 @@ class Stats(C.Structure):
     def as_dict(self):
         d = {k: int(getattr(self, k)) for k in self.COUNTER_FIELDS}
         d.update(exact_tests=int(self.exact_tests), status=int(self.status), first_bad_x=int(self.first_bad_x),
-                 first_bad_y=int(self.first_bad_y), max_stack=int(self.max_stack), device_ms=float(self.device_ms))
+                 first_bad_y=int(self.first_bad_y), max_stack=int(self.max_stack), device_ms=float(self.device_ms), trace_ms=float(self.trace_ms))
         return d

@@ -74,7 +74,7 @@ struct DevBuf {
 struct rtrb_renderer {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
   // baked scene
   int n_objects = 0, n_lights = 0;
   double max_distance = 0, soft_shadow_exponent = 0;
@@ -470,7 +470,9 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     g_launches++;
   }
   if (n_tiles > 0) {
+    CUDA_TRY(cudaEventRecord(r->evt0, stream));
     CUDA_TRY(strict ? rtrb_launch_trace_pre_strict(P, stack_need, stream) : rtrb_launch_trace_pre_fast(P, stack_need, stream));
+    CUDA_TRY(cudaEventRecord(r->evt1, stream));
     g_launches++;
     resolve_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
@@ -530,6 +532,10 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
     stats_out->device_ms = ms;
+    if (n_tiles > 0) {
+      CUDA_TRY(cudaEventElapsedTime(&ms, r->evt0, r->evt1));
+      stats_out->trace_ms = ms;
+    }
     if (st[0]) {
       fail(RTRB_ERR_RAISED, "the reference would have raised: status 0x%x at pixel (%d, %d)", st[0],
            stats_out->first_bad_x, stats_out->first_bad_y);
@@ -573,7 +579,8 @@ int rtrb_renderer_create(const rtrb_scene_desc* scene, int device, rtrb_renderer
   r->device = device;
   cudaError_t ce;
   if ((ce = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (ce = cudaEventCreate(&r->ev0)) != cudaSuccess || (ce = cudaEventCreate(&r->ev1)) != cudaSuccess) {
+      (ce = cudaEventCreate(&r->ev0)) != cudaSuccess || (ce = cudaEventCreate(&r->ev1)) != cudaSuccess ||
+      (ce = cudaEventCreate(&r->evt0)) != cudaSuccess || (ce = cudaEventCreate(&r->evt1)) != cudaSuccess) {
     delete r;
     return fail(RTRB_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(ce));
   }
@@ -593,6 +600,8 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   for (uint8_t* t : r->textures) cudaFree(t);
   if (r->ev0) cudaEventDestroy(r->ev0);
   if (r->ev1) cudaEventDestroy(r->ev1);
+  if (r->evt0) cudaEventDestroy(r->evt0);
+  if (r->evt1) cudaEventDestroy(r->evt1);
   if (r->stream) cudaStreamDestroy(r->stream);
   delete r;
   return RTRB_OK;
@@ -743,6 +752,7 @@ int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_
       agg.status |= st[i].status;
       agg.max_stack = std::max(agg.max_stack, st[i].max_stack);
       agg.device_ms = std::max(agg.device_ms, st[i].device_ms);
+      agg.trace_ms = std::max(agg.trace_ms, st[i].trace_ms);
       if (st[i].first_bad_x >= 0) {
         long long key = (long long)st[i].first_bad_x * cam->height + st[i].first_bad_y;
         if (best_key < 0 || key < best_key) { best_key = key; agg.first_bad_x = st[i].first_bad_x; agg.first_bad_y = st[i].first_bad_y; }
