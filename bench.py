@@ -53,20 +53,20 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                                "--format=csv,noheader,nounits"], timeout=5).decode()
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
@@ -159,7 +159,8 @@ def run_ours(args, rank, local_rank, world_size):
         dist.broadcast(hbuf, 0)
         if rank != 0:
             peer_ptr = ipc_open(local_rank, bytes(hbuf.cpu().numpy().tobytes()))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-NULL) stream: NULL means "the renderer's own stream" in the C ABI
+    torch.cuda.set_stream(stream)
 
     def opts(detail=False):
         return make_opts(seed=1, precision=precision, tile_rank=rank, tile_world=world_size, count_detail=detail,

@@ -81,6 +81,12 @@ struct rtrb_renderer {
   DevBuf<DevGeom> geom;
   DevBuf<DevMat> mat;
   DevBuf<DevLight> lights;
+  // FP32 filter view (FAST64)
+  DevBuf<float4> cull_sph, cull_pl;
+  DevBuf<int32_t> sph_index, pl_index;
+  DevBuf<DevLightF> lights_f;
+  int n_sph = 0, n_pl = 0;
+  float m_scene = 0.0f, max_distance_f = 0.0f;
   std::vector<uint8_t*> textures;
   // per-frame scratch
   DevBuf<int32_t> tiles;
@@ -319,6 +325,52 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
     d.radius = l.radius;
     d.hl_threshold = l.high_light_angle / 180.0 * 3.141592653589793;  // world.rb:92
   }
+  // ---- FP32 filter view: conversions round to nearest; the filter's margins cover that error ----
+  std::vector<float4> csph, cpl;
+  std::vector<int32_t> isph, ipl;
+  float m_scene = 0.0f;
+  for (int i = 0; i < s->n_objects; ++i) {
+    const rtrb_object_desc& o = s->objects[i];
+    if (o.type == RTRB_OBJ_SPHERE) {
+      csph.push_back(make_float4((float)o.point[0], (float)o.point[1], (float)o.point[2], (float)o.radius));
+      isph.push_back(i);
+      double cm = fmax(fabs(o.point[0]), fmax(fabs(o.point[1]), fabs(o.point[2]))) + fabs(o.radius);
+      m_scene = fmaxf(m_scene, nextafterf((float)cm, INFINITY));
+    } else {
+      double n1 = fabs(o.front[0]) + fabs(o.front[1]) + fabs(o.front[2]);
+      double pm = fmax(fabs(o.point[0]), fmax(fabs(o.point[1]), fabs(o.point[2])));
+      cpl.push_back(make_float4((float)o.front[0], (float)o.front[1], (float)o.front[2], nextafterf((float)n1, INFINITY)));
+      cpl.push_back(make_float4((float)o.point[0], (float)o.point[1], (float)o.point[2], nextafterf((float)pm, INFINITY)));
+      ipl.push_back(i);
+    }
+  }
+  r->n_sph = (int)isph.size(); r->n_pl = (int)ipl.size();
+  r->m_scene = m_scene;
+  r->max_distance_f = nextafterf((float)s->max_distance, INFINITY);
+  std::vector<DevLightF> lf(s->n_lights);
+  for (int i = 0; i < s->n_lights; ++i) {
+    const rtrb_light_desc& l = s->lights[i];
+    double thr = l.high_light_angle / 180.0 * 3.141592653589793;
+    lf[i].px = (float)l.position[0]; lf[i].py = (float)l.position[1]; lf[i].pz = (float)l.position[2];
+    lf[i].pmax = nextafterf((float)fmax(fabs(l.position[0]), fmax(fabs(l.position[1]), fabs(l.position[2]))), INFINITY);
+    lf[i].mode = (thr > 1e-4 && thr < 1.5) ? 1 : 0;
+    double c = cos(thr);
+    lf[i].cos2_thr = (float)(c * c);
+  }
+  CUDA_TRY(r->cull_sph.ensure(std::max<size_t>(1, csph.size())));
+  CUDA_TRY(r->sph_index.ensure(std::max<size_t>(1, isph.size())));
+  CUDA_TRY(r->cull_pl.ensure(std::max<size_t>(1, cpl.size())));
+  CUDA_TRY(r->pl_index.ensure(std::max<size_t>(1, ipl.size())));
+  CUDA_TRY(r->lights_f.ensure(std::max<size_t>(1, lf.size())));
+  if (!csph.empty()) {
+    CUDA_TRY(cudaMemcpy(r->cull_sph.p, csph.data(), csph.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->sph_index.p, isph.data(), isph.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  if (!ipl.empty()) {
+    CUDA_TRY(cudaMemcpy(r->cull_pl.p, cpl.data(), cpl.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->pl_index.p, ipl.data(), ipl.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  if (!lf.empty()) CUDA_TRY(cudaMemcpy(r->lights_f.p, lf.data(), lf.size() * sizeof(DevLightF), cudaMemcpyHostToDevice));
   CUDA_TRY(r->geom.ensure(std::max(1, s->n_objects)));
   CUDA_TRY(r->mat.ensure(std::max(1, s->n_objects)));
   CUDA_TRY(r->lights.ensure(std::max(1, s->n_lights)));
@@ -450,6 +502,9 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.max_distance = r->max_distance; P.soft_shadow_exponent = r->soft_shadow_exponent;
   P.n_objects = r->n_objects; P.n_lights = r->n_lights;
   P.geom = r->geom.p; P.mat = r->mat.p; P.lights = r->lights.p;
+  P.cull_sph = r->cull_sph.p; P.sph_index = r->sph_index.p; P.cull_pl = r->cull_pl.p; P.pl_index = r->pl_index.p;
+  P.lights_f = r->lights_f.p; P.n_sph = r->n_sph; P.n_pl = r->n_pl;
+  P.m_scene = r->m_scene; P.max_distance_f = r->max_distance_f;
   P.key0 = (uint32_t)opts.seed; P.key1 = (uint32_t)(opts.seed >> 32);
   P.x0 = x0; P.y0 = y0; P.x1 = x1; P.y1 = y1;
   P.n_tiles = n_tiles; P.stx_count = stx_count; P.tiles = r->tiles.p;
@@ -594,7 +649,8 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   if (!r) return RTRB_OK;
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
-  r->geom.release(); r->mat.release(); r->lights.release(); r->tiles.release(); r->samples.release();
+  r->geom.release(); r->mat.release(); r->lights.release();
+  r->cull_sph.release(); r->cull_pl.release(); r->sph_index.release(); r->pl_index.release(); r->lights_f.release(); r->tiles.release(); r->samples.release();
   r->extra_samples.release(); r->rgb.release(); r->extra_list.release(); r->hit.release(); r->rgba.release();
   r->counters.release(); r->status.release();
   for (uint8_t* t : r->textures) cudaFree(t);

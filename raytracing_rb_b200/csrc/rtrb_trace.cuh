@@ -133,57 +133,68 @@ __device__ __forceinline__ bool plane_intersect(const DevGeom& g, d3 o, d3 d, Hi
   return true;
 }
 
+// Probe ray of cover_area (world_object.rb:42): from `target` towards the light, unnormalised.
+struct CoverRay {
+  d3 target, lp, lt, ltn, tl;
+  double lt_r;
+};
+__device__ __forceinline__ CoverRay make_cover_ray(d3 target, const DevLight& L) {
+  CoverRay c;
+  c.target = target;
+  c.lp = mk(L.px, L.py, L.pz);
+  c.lt = c.lp - target;
+  c.lt_r = norm(c.lt);
+  c.ltn = mk(c.lt.x / c.lt_r, c.lt.y / c.lt_r, c.lt.z / c.lt_r);
+  c.tl = target - c.lp;
+  return c;
+}
+
+// cover_area of ONE object, exactly as the reference evaluates it:
+// Sphere#cover_area (sphere.rb:28-57) / WorldObject#cover_area (world_object.rb:41-49).
+__device__ __forceinline__ double cover_object_exact(const DevGeom& g, const CoverRay& c, double light_radius,
+                                                     ThreadCtx& ctx) {
+  if (g.type == RTRB_OBJ_SPHERE) {
+    RTRB_COUNT(ctx, RTRB_CNT_COV_SPH);
+    HitRec h;
+    int factor = 0;
+    if (sphere_intersect(g, c.target, c.lt, c.lt_r, c.ltn, h) && dot(h.p - c.lp, c.tl) > 0) factor = 1;
+    d3 cc = mk(g.px, g.py, g.pz);
+    double t = dot(cc - c.target, c.lt) / (c.lt_r * c.lt_r);
+    d3 x1 = c.target + c.lt * t;
+    double r1 = light_radius * (norm(x1 - c.target) / c.lt_r);
+    double dd = norm(x1 - cc);
+    if (dd >= r1 + g.radius) return 0;
+    double s1 = RTRB_PI * r1 * r1;
+    if (dd > fabs(g.radius - r1)) {
+      RTRB_COUNT(ctx, RTRB_CNT_COV_SPH_PEN);
+      double ct1 = fmin((r1 * r1 + dd * dd - g.radius * g.radius) / (2 * r1 * dd), 1.0);
+      double ct2 = fmin((g.radius * g.radius + dd * dd - r1 * r1) / (2 * g.radius * dd), 1.0);
+      double th1 = rb_acos(ct1, ctx), th2 = rb_acos(ct2, ctx);
+      double delta_s = ((th1 - sin(th1)) * r1 * r1 + (th2 - sin(th2)) * g.radius * g.radius) / 2;
+      return factor * delta_s / s1;
+    }
+    RTRB_COUNT(ctx, RTRB_CNT_COV_SPH_FULL);
+    if (r1 > g.radius) return factor * RTRB_PI * g.radius * g.radius / s1;
+    return factor;
+  }
+  RTRB_COUNT(ctx, RTRB_CNT_COV_PL);
+  HitRec h;
+  double den;
+  if (plane_intersect(g, c.target, c.lt, h, den) && dot(h.p - c.lp, c.tl) > 0) {
+    RTRB_COUNT(ctx, RTRB_CNT_COV_PL_ACC);
+    return 1;
+  }
+  return 0;
+}
+
 // World#lit_area (world.rb:62-69) for one light seen from `target`:
 // max(1 - sum over ALL objects of cover_area, 0), subtraction in world_objects order.
-__device__ __noinline__ double lit_area(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
-  d3 lp = mk(L.px, L.py, L.pz);
-  d3 lt = lp - target;           // ray.front of cover_area's probe ray (world_object.rb:42)
-  double lt_r = norm(lt);
-  d3 ltn = mk(lt.x / lt_r, lt.y / lt_r, lt.z / lt_r);
-  d3 tl = target - lp;
+static __device__ __noinline__ double lit_area(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
+  const CoverRay c = make_cover_ray(target, L);
   double total = 1;
   for (int i = 0; i < P.n_objects; ++i) {
     const DevGeom g = P.geom[i];
-    double cover;
-    if (g.type == RTRB_OBJ_SPHERE) {
-      RTRB_COUNT(ctx, RTRB_CNT_COV_SPH);
-      // factor = WorldObject#cover_area (world_object.rb:41-49) via Sphere#intersect
-      HitRec h;
-      int factor = 0;
-      if (sphere_intersect(g, target, lt, lt_r, ltn, h) && dot(h.p - lp, tl) > 0) factor = 1;
-      // Sphere#cover_area (sphere.rb:28-57)
-      d3 c = mk(g.px, g.py, g.pz);
-      double t = dot(c - target, lt) / (lt_r * lt_r);
-      d3 x1 = target + lt * t;
-      double r1 = L.radius * (norm(x1 - target) / lt_r);
-      double dd = norm(x1 - c);
-      if (dd >= r1 + g.radius) {
-        cover = 0;
-      } else {
-        double s1 = RTRB_PI * r1 * r1;
-        if (dd > fabs(g.radius - r1)) {
-          RTRB_COUNT(ctx, RTRB_CNT_COV_SPH_PEN);
-          double ct1 = fmin((r1 * r1 + dd * dd - g.radius * g.radius) / (2 * r1 * dd), 1.0);
-          double ct2 = fmin((g.radius * g.radius + dd * dd - r1 * r1) / (2 * g.radius * dd), 1.0);
-          double th1 = rb_acos(ct1, ctx), th2 = rb_acos(ct2, ctx);
-          double delta_s = ((th1 - sin(th1)) * r1 * r1 + (th2 - sin(th2)) * g.radius * g.radius) / 2;
-          cover = factor * delta_s / s1;
-        } else {
-          RTRB_COUNT(ctx, RTRB_CNT_COV_SPH_FULL);
-          if (r1 > g.radius) cover = factor * RTRB_PI * g.radius * g.radius / s1;
-          else cover = factor;
-        }
-      }
-    } else {
-      RTRB_COUNT(ctx, RTRB_CNT_COV_PL);
-      HitRec h; double den;
-      cover = 0;
-      if (plane_intersect(g, target, lt, h, den) && dot(h.p - lp, tl) > 0) {
-        cover = 1;
-        RTRB_COUNT(ctx, RTRB_CNT_COV_PL_ACC);
-      }
-    }
-    total -= cover;
+    total -= cover_object_exact(g, c, L.radius, ctx);
   }
   return fmax(total, 0.0);
 }
@@ -432,7 +443,7 @@ __device__ __forceinline__ void lens_ray(const FrameParams& P, int x, int y, dou
   double sx = 2.0 * ((double)x / P.width - 0.5) * P.retina_width;
   double sy = 2 * ((double)y / P.height - 0.5) * P.retina_height;
   d3 retina_position = (ld3(P.retina_center) + left * sx) + upn * sy;
-  d3 rand_vector = (ld3(P.left_n) * cos(theta) + upn * sin(theta)) * P.aperture_radius;
+  d3 rand_vector = (ld3(P.left_n) * cos(theta) + upn * sin(theta)) * P.aperture_radius;  // (finite)*0.0 when pinhole
   d3 aperture = pos + rand_vector;
   d3 rf = pos - retina_position;  // ray retina -> lens centre
   double t = dot(ld3(P.focal_point) - retina_position, front) / dot(front, rf);  // intersect_plane :123-127
@@ -489,8 +500,20 @@ __device__ __forceinline__ void init_ctx(ThreadCtx& ctx, bool detail) {
   for (int i = 0; i < RTRB_CNT_N; ++i) ctx.c[i] = 0;
 }
 
+// FAST64 entry point, defined in rtrb_trace_fast.cuh (only instantiated by that translation unit).
+template <int MAXS>
+__device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
+                                                ThreadCtx& ctx, int* primary_hit);
+
+template <int MAXS, bool FAST>
+__device__ __forceinline__ d3 trace_dispatch(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
+                                             ThreadCtx& ctx, int* primary_hit) {
+  if constexpr (FAST) return trace_sample_fast<MAXS>(P, ro, rd, pixel, sample, ctx, primary_hit);
+  else return trace_sample<MAXS>(P, ro, rd, pixel, sample, ctx, primary_hit);
+}
+
 // One thread per (pixel, sample j < pre_sample_times): the first loop of render_at (camera.rb:73-78).
-template <int MAXS, bool DETAIL>
+template <int MAXS, bool DETAIL, bool FAST = false>
 __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
   const uint32_t S = (uint32_t)P.pre;
   const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -510,7 +533,7 @@ __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
       d3 ro, rd;
       lens_ray(P, x, y, theta, ro, rd);
       int ph;
-      d3 col = trace_sample<MAXS>(P, ro, rd, pixel, j, ctx, &ph);
+      d3 col = trace_dispatch<MAXS, FAST>(P, ro, rd, pixel, j, ctx, &ph);
       RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
       double* out = P.samples + w * 3ull;
       out[0] = col.x; out[1] = col.y; out[2] = col.z;
@@ -522,7 +545,7 @@ __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
 
 // Extra samples j in [pre, max) of the pixels that failed the variance test (camera.rb:88-93);
 // persistent grid-stride loop because the pixel count is only known on the device.
-template <int MAXS, bool DETAIL>
+template <int MAXS, bool DETAIL, bool FAST = false>
 __device__ __forceinline__ void trace_extra_body(const FrameParams& P) {
   const uint32_t E = (uint32_t)(P.max_samples - P.pre);
   const unsigned long long total = (unsigned long long)(*P.extra_count) * E;
@@ -543,7 +566,7 @@ __device__ __forceinline__ void trace_extra_body(const FrameParams& P) {
     d3 ro, rd;
     lens_ray(P, x, y, theta, ro, rd);
     int ph;
-    d3 col = trace_sample<MAXS>(P, ro, rd, pixel, j, ctx, &ph);
+    d3 col = trace_dispatch<MAXS, FAST>(P, ro, rd, pixel, j, ctx, &ph);
     RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
     double* out = P.extra_samples + w * 3ull;
     out[0] = col.x; out[1] = col.y; out[2] = col.z;

@@ -1,10 +1,52 @@
-// rtrb_trace_fast.cu — RTRB_PREC_FAST64.  Placeholder routing: until the FP32-cull + exact-FP64
-// refine kernels land, FAST64 runs the STRICT kernels (identical results by definition of the mode).
+// rtrb_trace_fast.cu — RTRB_PREC_FAST64 instantiation (FP32 filter + exact FP64 refine).
+// Compiled with -fmad=false: the exact parts must round like STRICT; the filter uses explicit fmaf().
 #include "rtrb_launch.h"
+#include "rtrb_trace_fast.cuh"
+
+namespace {
+
+constexpr int kBlock = 128;
+
+template <int MAXS, bool DETAIL>
+__global__ void __launch_bounds__(kBlock) trace_pre_fast_kernel(const __grid_constant__ FrameParams P) {
+  rtrb::trace_pre_body<MAXS, DETAIL, true>(P);
+}
+template <int MAXS, bool DETAIL>
+__global__ void __launch_bounds__(kBlock) trace_extra_fast_kernel(const __grid_constant__ FrameParams P) {
+  rtrb::trace_extra_body<MAXS, DETAIL, true>(P);
+}
+
+template <int MAXS, bool DETAIL>
+cudaError_t launch_pre(const FrameParams& P, cudaStream_t s) {
+  unsigned long long total = (unsigned long long)P.n_tiles * RTRB_SUPER_PIXELS * (unsigned long long)P.pre;
+  if (total == 0) return cudaSuccess;
+  unsigned long long blocks = (total + kBlock - 1) / kBlock;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  trace_pre_fast_kernel<MAXS, DETAIL><<<(unsigned)blocks, kBlock, 0, s>>>(P);
+  return cudaGetLastError();
+}
+template <int MAXS, bool DETAIL>
+cudaError_t launch_extra(const FrameParams& P, cudaStream_t s) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  trace_extra_fast_kernel<MAXS, DETAIL><<<sms * 8, kBlock, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+#define RTRB_DISPATCH(fn, P, need, s)                                         \
+  do {                                                                        \
+    const bool det = (P).count_detail != 0;                                   \
+    if ((need) <= 10) return det ? fn<10, true>(P, s) : fn<10, false>(P, s);  \
+    if ((need) <= 32) return det ? fn<32, true>(P, s) : fn<32, false>(P, s);  \
+    return det ? fn<128, true>(P, s) : fn<128, false>(P, s);                  \
+  } while (0)
 
 cudaError_t rtrb_launch_trace_pre_fast(const FrameParams& P, int stack_need, cudaStream_t s) {
-  return rtrb_launch_trace_pre_strict(P, stack_need, s);
+  RTRB_DISPATCH(launch_pre, P, stack_need, s);
 }
 cudaError_t rtrb_launch_trace_extra_fast(const FrameParams& P, int stack_need, cudaStream_t s) {
-  return rtrb_launch_trace_extra_strict(P, stack_need, s);
+  RTRB_DISPATCH(launch_extra, P, stack_need, s);
 }

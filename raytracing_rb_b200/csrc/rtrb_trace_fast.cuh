@@ -1,0 +1,443 @@
+// rtrb_trace_fast.cuh — RTRB_PREC_FAST64: the same ray tree, evaluated "filter then exact".
+//
+// Every per-object decision of the reference (does object i win World#intersect, does object i
+// contribute to lit_area, does a light match the highlight test) is first bounded in FP32 with a
+// rigorous error margin; only the objects the filter cannot exclude are re-evaluated with the
+// STRICT FP64 functions of rtrb_trace.cuh, in world_objects order.  Objects the filter excludes
+// contribute exactly what the reference computes for them (no hit / cover 0 / no match), so the
+// frame is bit-identical to STRICT; the filter only removes FP64 work (DESIGN.md "FAST64").
+//
+// Compiled with -fmad=false as well: the exact parts must not contract, the FP32 filter uses
+// explicit fmaf().
+#pragma once
+#include "rtrb_trace.cuh"
+
+namespace rtrb {
+
+#define RTRB_CMAX 8  // candidates kept per query before falling back to the exact scan
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// A ray as the FP32 filter sees it: origin, UNIT direction, and E = 64 * 2^-24 * (M_scene + |O|_inf),
+// an absolute bound on the FP32 error of every length the filter forms (derivation in DESIGN.md).
+struct CullRay {
+  float ox, oy, oz, dx, dy, dz, E;
+};
+__device__ __forceinline__ CullRay make_cull_ray(const FrameParams& P, d3 o, d3 dn) {
+  CullRay r;
+  r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
+  r.dx = (float)dn.x; r.dy = (float)dn.y; r.dz = (float)dn.z;
+  float m = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
+  r.E = 3.8146973e-6f * (P.m_scene + m);  // 64 * 2^-24
+  return r;
+}
+
+// Sphere filter. Returns 0 = certainly no hit, 1 = possible hit (lo valid), 2 = certain hit (lo, hi valid).
+// lo/hi bound Ray#distance(intersection) of Sphere#intersect (sphere.rb:60-85).
+__device__ __forceinline__ int cull_sphere(const float4 s, const CullRay& r, float& lo, float& hi) {
+  const float ocx = s.x - r.ox, ocy = s.y - r.oy, ocz = s.z - r.oz;
+  const float b = fmaf(ocz, r.dz, fmaf(ocy, r.dy, ocx * r.dx));
+  const float qx = fmaf(-b, r.dx, ocx), qy = fmaf(-b, r.dy, ocy), qz = fmaf(-b, r.dz, ocz);
+  const float m2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
+  const float Rp = s.w + r.E;
+  if (m2 > Rp * Rp) return 0;  // the line passes the centre farther than R (+ margin)
+  const float oc2 = fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx));
+  const float Rm = fmaxf(s.w - r.E, 0.0f);
+  const bool outside = oc2 > Rp * Rp;
+  const bool inside = oc2 < Rm * Rm;
+  if (outside && b < -r.E) return 0;  // centre behind an outside origin: `!from_inner && t < 0`
+  const float m = sqrt_approx(m2);
+  const float mlo = fmaxf(m - r.E, 0.0f), mhi = m + r.E;
+  const float h_hi = sqrt_approx(fmaxf(fmaf(Rp, Rp, -mlo * mlo), 0.0f)) * 1.000001f + r.E;
+  const float h_lo = sqrt_approx(fmaxf(fmaf(Rm, Rm, -mhi * mhi), 0.0f)) * 0.999999f;
+  int kind;
+  if (outside) {
+    lo = b - h_hi - r.E;
+    hi = b - h_lo + r.E;
+    kind = (mhi < Rm && b > r.E) ? 2 : 1;
+  } else if (inside) {
+    lo = b + h_lo - r.E;
+    hi = b + h_hi + r.E;
+    kind = 2;
+  } else {
+    lo = b - h_hi - r.E;  // origin within the margin of the surface: either root is possible
+    hi = 0.0f;
+    kind = 1;
+  }
+  lo = fmaxf(lo, 0.0f);
+  if (!(lo == lo) || !(hi == hi)) { lo = 0.0f; kind = 1; }  // NaN anywhere: leave it to the exact test
+  return kind;
+}
+
+// Plane filter, same contract; a = (n, |n|_1), p = (P, |P|_inf).  Plane#intersect (plane.rb:38-51).
+__device__ __forceinline__ int cull_plane(const float4 a, const float4 p, const CullRay& r, float& lo, float& hi) {
+  const float eps = 5.9604645e-8f;  // 2^-24
+  const float den = fmaf(a.z, r.dz, fmaf(a.y, r.dy, a.x * r.dx));
+  const float rx = p.x - r.ox, ry = p.y - r.oy, rz = p.z - r.oz;
+  const float num = fmaf(rz, a.z, fmaf(ry, a.y, rx * a.x));
+  const float mo = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
+  const float e_num = 16.0f * eps * a.w * (p.w + mo);
+  const float e_den = 8.0f * eps * a.w;
+  const float aden = fabsf(den);
+  if (!(aden > 16.0f * e_den)) { lo = 0.0f; hi = 0.0f; return 1; }  // grazing (or NaN): exact test decides
+  const float inv = rcp_approx(den);
+  const float t = num * inv;
+  // |den_true| >= 15/16 |den| here, hence the 1.1
+  const float e_t = (e_num + fabsf(t) * e_den) * fabsf(inv) * 1.1f + 4.0f * eps * fabsf(t);
+  if (t + e_t < 0.0f) return 0;
+  lo = fmaxf(t - e_t, 0.0f);
+  hi = t + e_t;
+  if (!(lo == lo) || !(hi == hi)) { lo = 0.0f; return 1; }
+  return (t - e_t > 0.0f) ? 2 : 1;
+}
+
+struct CandList {
+  int n;
+  bool overflow;
+  int idx[RTRB_CMAX];
+  float lo[RTRB_CMAX];
+  __device__ __forceinline__ void clear() { n = 0; overflow = false; }
+  __device__ __forceinline__ void push(int i, float l) {
+    if (n < RTRB_CMAX) { idx[n] = i; lo[n] = l; n++; }
+    else overflow = true;
+  }
+  // ascending world_objects index (insertion sort; n <= 8)
+  __device__ __forceinline__ void sort_by_index() {
+    for (int a = 1; a < n; ++a) {
+      int ki = idx[a]; float kl = lo[a];
+      int b = a - 1;
+      while (b >= 0 && idx[b] > ki) { idx[b + 1] = idx[b]; lo[b + 1] = lo[b]; --b; }
+      idx[b + 1] = ki; lo[b + 1] = kl;
+    }
+  }
+};
+
+// World#intersect (world.rb:37-59) = FP32 filter over every object + exact test of the survivors.
+__device__ __forceinline__ int closest_hit_fast(const FrameParams& P, d3 o, d3 d, double d_r, d3 dn, HitRec& bh,
+                                                ThreadCtx& ctx) {
+  const CullRay r = make_cull_ray(P, o, dn);
+  CandList cl;
+  cl.clear();
+  float best_hi = P.max_distance_f;  // no object at or beyond max_distance can win (initial nearest_dis)
+  for (int k = 0; k < P.n_sph; ++k) {
+    const float4 s = __ldg(&P.cull_sph[k]);
+    float lo, hi;
+    const int kind = cull_sphere(s, r, lo, hi);
+    if (kind != 0 && lo <= best_hi) {
+      cl.push(P.sph_index[k], lo);
+      if (kind == 2) best_hi = fminf(best_hi, hi);
+    }
+  }
+  for (int k = 0; k < P.n_pl; ++k) {
+    const float4 a = __ldg(&P.cull_pl[2 * k]), p = __ldg(&P.cull_pl[2 * k + 1]);
+    float lo, hi;
+    const int kind = cull_plane(a, p, r, lo, hi);
+    if (kind != 0 && lo <= best_hi) {
+      cl.push(P.pl_index[k], lo);
+      if (kind == 2) best_hi = fminf(best_hi, hi);
+    }
+  }
+  double best = P.max_distance;
+  int best_i = -1;
+  if (!cl.overflow) {
+    // exact evaluation of the survivors; (distance, index) lexicographic == strict `<` in index order
+    for (int c = 0; c < cl.n; ++c) {
+      if (!(cl.lo[c] <= best_hi)) continue;
+      const int i = cl.idx[c];
+      const DevGeom g = P.geom[i];
+      HitRec h;
+      bool ok;
+      double den;
+      if (g.type == RTRB_OBJ_SPHERE) ok = sphere_intersect(g, o, d, d_r, dn, h);
+      else ok = plane_intersect(g, o, d, h, den);
+      RTRB_COUNT(ctx, RTRB_CNT_EXACT);
+      if (ok) {
+        const double new_dis = norm(o - h.p);
+        if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; bh = h; }
+      }
+    }
+    return best_i;
+  }
+  // more survivors than the list holds (rare): the reference's own scan
+  for (int i = 0; i < P.n_objects; ++i) {
+    const DevGeom g = P.geom[i];
+    HitRec h;
+    bool ok;
+    double den;
+    if (g.type == RTRB_OBJ_SPHERE) ok = sphere_intersect(g, o, d, d_r, dn, h);
+    else ok = plane_intersect(g, o, d, h, den);
+    RTRB_COUNT(ctx, RTRB_CNT_EXACT);
+    if (ok) {
+      const double new_dis = norm(o - h.p);
+      if (new_dis < best) { best = new_dis; best_i = i; bh = h; }
+    }
+  }
+  return best_i;
+}
+
+// World#lit_area (world.rb:62-69) = filter + exact cover of the survivors, subtracted in index order.
+// An object the probe ray certainly misses (or certainly meets beyond the light) has factor 0, hence
+// cover exactly 0 (sphere.rb:29,45-53 multiply everything by factor; world_object.rb:43-47).
+__device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
+  const CoverRay c = make_cover_ray(target, L);
+  const CullRay r = make_cull_ray(P, target, c.ltn);
+  const float ell = (float)c.lt_r;
+  const float far = ell * 1.00001f + 2.0f * r.E;  // hits farther than the light cannot cover
+  CandList cl;
+  cl.clear();
+  for (int k = 0; k < P.n_sph; ++k) {
+    const float4 s = __ldg(&P.cull_sph[k]);
+    float lo, hi;
+    const int kind = cull_sphere(s, r, lo, hi);
+    if (kind != 0 && !(lo > far)) cl.push(P.sph_index[k], lo);
+  }
+  for (int k = 0; k < P.n_pl; ++k) {
+    const float4 a = __ldg(&P.cull_pl[2 * k]), p = __ldg(&P.cull_pl[2 * k + 1]);
+    float lo, hi;
+    const int kind = cull_plane(a, p, r, lo, hi);
+    if (kind != 0 && !(lo > far)) cl.push(P.pl_index[k], lo);
+  }
+  double total = 1;
+  if (!cl.overflow) {
+    cl.sort_by_index();
+    for (int k = 0; k < cl.n; ++k) {
+      const DevGeom g = P.geom[cl.idx[k]];
+      RTRB_COUNT(ctx, RTRB_CNT_EXACT);
+      total -= cover_object_exact(g, c, L.radius, ctx);
+    }
+  } else {
+    for (int i = 0; i < P.n_objects; ++i) {
+      const DevGeom g = P.geom[i];
+      RTRB_COUNT(ctx, RTRB_CNT_EXACT);
+      total -= cover_object_exact(g, c, L.radius, ctx);
+    }
+  }
+  return fmax(total, 0.0);
+}
+
+// World#high_lights match for one light (world.rb:86-93): acos(|cos|) < threshold, filtered in FP32 on
+// cos^2 against cos^2(threshold); the exact FP64 expression decides only inside the error band.
+__device__ __forceinline__ bool highlight_match_fast(const DevLight& L, const DevLightF& F, d3 o, d3 d,
+                                                     const CullRay& r, ThreadCtx& ctx) {
+  const float eps = 5.9604645e-8f;
+  const float ax = F.px - r.ox, ay = F.py - r.oy, az = F.pz - r.oz;
+  const float ret = fmaf(az, r.dz, fmaf(ay, r.dy, ax * r.dx));
+  const float a2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
+  const float mo = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
+  const float ea = 8.0f * eps * (F.pmax + mo);
+  const float c2 = ret * ret * rcp_approx(a2);
+  const float rho = 8.0f * (ea * rsqrtf(a2) + 8.0f * eps);  // absolute error bound on |cos| (<= 1)
+  const float tol = fmaf(rho, rho, 2.0f * rho);              // ... hence on cos^2
+  if (F.mode == 1 && rho < 0.25f) {
+    if (c2 - tol > F.cos2_thr) return true;
+    if (c2 + tol < F.cos2_thr) return false;
+  }
+  // exact (also reached for thresholds outside (0, 90 degrees), NaNs, and rays starting at the light)
+  d3 a = mk(L.px, L.py, L.pz) - o;
+  double ct = vcos(d, a, ctx);
+  double ang = rb_acos(ct, ctx);
+  return ang < L.hl_threshold;
+}
+
+// RayTracer#trace_sync, FAST64 evaluation.  Same contract as trace_sample<MAXS> in rtrb_trace.cuh.
+template <int MAXS>
+__device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
+                                                ThreadCtx& ctx, int* primary_hit) {
+  StackItem stack[MAXS];
+  stack[0].ox = ro.x; stack[0].oy = ro.y; stack[0].oz = ro.z;
+  stack[0].dx = rd.x; stack[0].dy = rd.y; stack[0].dz = rd.z;
+  stack[0].ax = 1.0; stack[0].ay = 1.0; stack[0].az = 1.0;
+  stack[0].depth = P.trace_depth; stack[0].path = 1u;
+  int sp = 1;
+  d3 sum = mk(0.0, 0.0, 0.0);
+  bool first = true;
+  const uint32_t K = (uint32_t)(P.mc + 2);
+  *primary_hit = -1;
+
+  while (sp > 0) {
+    if ((uint32_t)sp > ctx.max_stack) ctx.max_stack = (uint32_t)sp;
+    const StackItem it = stack[--sp];
+    const bool is_first = first;
+    first = false;
+    const d3 o = mk(it.ox, it.oy, it.oz), d = mk(it.dx, it.dy, it.dz), att = mk(it.ax, it.ay, it.az);
+    if (it.depth <= 0 || norm(att) < 0.0001) continue;  // rt_map :52
+    ctx.rays++;
+
+    const double d_r = norm(d);
+    const d3 dn = mk(d.x / d_r, d.y / d_r, d.z / d_r);
+
+    // ---- World#high_lights ----
+    {
+      const CullRay r = make_cull_ray(P, o, dn);
+      unsigned long long hl_mask = 0ull;
+      int hl_n = 0;
+      for (int l = 0; l < P.n_lights; ++l)
+        if (highlight_match_fast(P.lights[l], P.lights_f[l], o, d, r, ctx)) { hl_mask |= 1ull << l; hl_n++; }
+      if (hl_n > 0) {
+        for (int l = 0; l < P.n_lights; ++l) {
+          if (!((hl_mask >> l) & 1ull)) continue;
+          d3 c = (att * ld3(P.lights[l].color_hl)) / (double)hl_n;
+          sum = sum + c;
+          if (sum.x > 1 || sum.y > 1 || sum.z > 1) ctx.status |= RTRB_ST_COLOR_GT_1;
+        }
+        RTRB_COUNT(ctx, RTRB_CNT_HIGHLIGHT);
+        if (is_first) *primary_hit = -2;
+        continue;
+      }
+    }
+
+    // ---- World#intersect ----
+    HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false;
+    const int best_i = closest_hit_fast(P, o, d, d_r, dn, bh, ctx);
+    if (best_i < 0) continue;
+    if (is_first) *primary_hit = best_i;
+    RTRB_COUNT(ctx, RTRB_CNT_HITS);
+
+    const DevGeom g = P.geom[best_i];
+    const DevMat& M = P.mat[best_i];
+    d3 n, delta;
+    double rate;
+    bool can_refract;
+    if (g.type == RTRB_OBJ_SPHERE) {
+      d3 c = mk(g.px, g.py, g.pz);
+      delta = ((bh.p - c) * RTRB_EPSILON) * (bh.dir_in ? 1.0 : -1.0);
+      n = bh.dir_in ? (bh.p - c) : (c - bh.p);
+      rate = bh.dir_in ? M.refractive_rate : 1.0 / M.refractive_rate;
+      can_refract = true;
+    } else {
+      d3 f = mk(g.nx, g.ny, g.nz);
+      double fd = dot(f, d);
+      double nfd = -fd;
+      double sgn = nfd > 0 ? 1.0 : (nfd < 0 ? -1.0 : 0.0);
+      delta = (f * RTRB_EPSILON) * sgn;
+      n = fd > 0 ? -f : f;
+      rate = M.refractive_rate;
+      can_refract = M.has_refraction != 0;
+    }
+    const d3 nn = normalize(n, ctx);
+
+    // ---- children (ray_tracer.rb:87-121), computed only if they can survive the cut at :52.
+    // A child with trace_depth - 1 <= 0, or whose attenuation norm is certainly < 1e-4, is popped and
+    // dropped by the reference without any observable effect; skipping its direction math changes
+    // nothing except in the one case where that math would RAISE (normalize of an exactly zero
+    // reflection + d, world_object.rb:136) — detected below by a cheap necessary condition.
+    const d3 a_refl = att * ld3(M.refl), a_refr = att * ld3(M.refr);
+    const bool depth_ok = it.depth - 1 > 0;
+    const bool refl_alive = depth_ok && !(sumsq(a_refl) < 0.99e-8);
+    const bool refr_alive = depth_ok && !(sumsq(a_refr) < 0.99e-8);
+    const double dn_dot = dot(d, n);
+    const bool near_normal = !(dn_dot * dn_dot < (1.0 - 1e-9) * (sumsq(d) * sumsq(n)));  // possible raise site
+    if (refl_alive || refr_alive || near_normal) {
+      if (sp + 2 > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; continue; }
+      const double cos_theta = vcos(d, -n, ctx);  // == vcos(d, n): both square the dot product
+      const d3 refl_dir = normalize(nn * (2 * cos_theta * d_r) + d, ctx);
+      if (refl_alive || near_normal) {
+        const d3 refl_org = bh.p + delta;
+        StackItem& s = stack[sp++];
+        s.ox = refl_org.x; s.oy = refl_org.y; s.oz = refl_org.z;
+        s.dx = refl_dir.x; s.dy = refl_dir.y; s.dz = refl_dir.z;
+        s.ax = a_refl.x; s.ay = a_refl.y; s.az = a_refl.z;
+        s.depth = it.depth - 1; s.path = it.path * K + 0u;
+      }
+      if (can_refract && (refr_alive || near_normal)) {
+        const double sin_i = rb_sqrt(1 - cos_theta * cos_theta, ctx);
+        const double sin_r = sin_i / rate;
+        if (!(sin_r >= 1)) {
+          if (sin_r < -1 || sin_r > 1) ctx.status |= RTRB_ST_MATH_DOMAIN;
+          const double rr = asin(sin_r);
+          const d3 refr_dir = nn * (-cos(rr)) + normalize(refl_dir + d, ctx) * sin_r;
+          const d3 refr_org = bh.p - nn * RTRB_EPSILON;
+          RTRB_COUNT(ctx, RTRB_CNT_REFR);
+          StackItem& s = stack[sp++];
+          s.ox = refr_org.x; s.oy = refr_org.y; s.oz = refr_org.z;
+          s.dx = refr_dir.x; s.dy = refr_dir.y; s.dz = refr_dir.z;
+          s.ax = a_refr.x; s.ay = a_refr.y; s.az = a_refr.z;
+          s.depth = it.depth - 1; s.path = it.path * K + 1u;
+        }
+      }
+    }
+
+    // ---- World#local_lights + WorldObject#local_lighting ----
+    const d3 shade_from = bh.p + delta;
+    d3 contrib = mk(0.0, 0.0, 0.0);
+    int n_lit = 0;
+    for (int l = 0; l < P.n_lights; ++l) {
+      const DevLight& L = P.lights[l];
+      ctx.shadow++;
+      const double area = lit_area_fast(P, shade_from, L, ctx);
+      if (area > 0) {
+        d3 lc = ld3(L.color) * (rb_pow(area, P.soft_shadow_exponent) / (double)P.n_lights);
+        d3 lv = normalize(mk(L.px, L.py, L.pz) - bh.p, ctx);
+        double ldn = dot(lv, nn);
+        if (ldn > 1) ldn = 1.0; else if (ldn < 0) ldn = 0.0;
+        contrib = contrib + lc * ldn;
+        n_lit++;
+      }
+    }
+    if (n_lit == 0) {
+      if (P.mc > 0) {
+        if (sp + P.mc > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; continue; }
+        const d3 att_pt = ld3(M.diffuse) / (double)P.mc;
+        const d3 a2 = att * att_pt;
+        const bool mc_alive = depth_ok && !(sumsq(a2) < 0.99e-8);
+        const d3 vv = a_vertical_vector(n, ctx);
+        if (mc_alive || norm(vv) == 0) {
+          const d3 leftv = normalize(vv, ctx);
+          const d3 upv = cross(nn, leftv);
+          for (int m = 0; m < P.mc; ++m) {
+            uint32_t child = it.path * K + (uint32_t)(2 + m);
+            uint32_t c0 = pixel, c1 = sample, c2 = child, c3 = 1u;
+            philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
+            double theta = res53(c0, c1) * RTRB_PI / 2, phi = res53(c2, c3) * RTRB_PI * 2;
+            d3 dir = nn * sin(theta) + (leftv * cos(phi) + upv * sin(phi)) * cos(theta);
+            StackItem& s = stack[sp++];
+            s.ox = shade_from.x; s.oy = shade_from.y; s.oz = shade_from.z;
+            s.dx = dir.x; s.dy = dir.y; s.dz = dir.z;
+            s.ax = a2.x; s.ay = a2.y; s.az = a2.z;
+            s.depth = it.depth - 1; s.path = child;
+          }
+        }
+        if (ctx.detail) ctx.c[RTRB_CNT_MC] += P.mc;
+      }
+    } else {
+      RTRB_COUNT(ctx, RTRB_CNT_LOCAL);
+      if (ctx.detail) ctx.c[RTRB_CNT_LIT] += n_lit;
+      contrib = contrib / (double)n_lit;
+      d3 filter = mk(1.0, 1.0, 1.0);
+      if (M.tex != nullptr) {
+        double u, v;
+        if (g.type == RTRB_OBJ_SPHERE) {
+          d3 vec = bh.p - mk(g.px, g.py, g.pz);
+          double x = dot(vec, ld3(M.e0)) / g.radius;
+          double y = dot(vec, ld3(M.e1)) / g.radius;
+          double z = dot(vec, ld3(M.e2)) / g.radius;
+          double mm = rb_sqrt(x * x + y * y + z * z + 2 * x + 1, ctx);
+          u = (y / mm + 1) / 2;
+          v = (-z / mm + 1) / 2;
+        } else {
+          d3 rel = bh.p - mk(g.px, g.py, g.pz);
+          u = dot(rel, ld3(M.e0)) / M.u_unit;
+          v = dot(rel, ld3(M.e1)) / M.v_unit;
+        }
+        RTRB_COUNT(ctx, RTRB_CNT_TEXEL);
+        filter = texture_color(M, u, v, ctx) * filter;
+      }
+      d3 local = ((contrib * ld3(M.diffuse)) * filter) + ld3(M.ambient);
+      d3 c = att * local;
+      sum = sum + c;
+      if (sum.x > 1 || sum.y > 1 || sum.z > 1) ctx.status |= RTRB_ST_COLOR_GT_1;
+    }
+  }
+  return sum;
+}
+
+}  // namespace rtrb

@@ -44,6 +44,14 @@ struct DevLight {
   double hl_threshold;  // high_light_angle / 180.0 * PI (world.rb:92)
 };
 
+// FP32 view of a light for the highlight filter (rtrb_trace_fast.cuh).
+struct DevLightF {
+  float px, py, pz;
+  float pmax;       // |position|_inf
+  float cos2_thr;   // cos^2(high_light_angle), valid when mode == 1
+  int32_t mode;     // 1: threshold in (0, 90 deg) -> FP32 filter usable; 0: always take the exact path
+};
+
 // Per-frame constants: thin-lens camera baked on the host in the reference's evaluation order
 // (camera.rb:129-151) + sampling + tiling.  Passed by value as a __grid_constant__ kernel parameter.
 struct FrameParams {
@@ -66,6 +74,15 @@ struct FrameParams {
   const DevGeom* geom;
   const DevMat* mat;
   const DevLight* lights;
+  // FP32 filter view (FAST64): spheres and planes split by type, original indices kept
+  const float4* cull_sph;      // [n_sph] (cx, cy, cz, R)
+  const int32_t* sph_index;    // [n_sph] index in world_objects
+  const float4* cull_pl;       // [2*n_pl] (nx, ny, nz, |n|_1), (px, py, pz, |P|_inf)
+  const int32_t* pl_index;     // [n_pl]
+  const DevLightF* lights_f;   // [n_lights]
+  int32_t n_sph, n_pl;
+  float m_scene;               // max over spheres of |C|_inf + R  (error-bound scale)
+  float max_distance_f;        // max_distance rounded up to float
   // rng
   uint32_t key0, key1;
   // work domain
