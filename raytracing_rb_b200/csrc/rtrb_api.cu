@@ -19,6 +19,7 @@
 
 #include "../../include/rtrb_b200.h"
 #include "rtrb_launch.h"
+#include "rtrb_trace.cuh"
 #include "rtrb_types.h"
 
 namespace {
@@ -109,28 +110,10 @@ struct rtrb_renderer {
 namespace {
 
 // ---- resolve kernels ---------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t quantise(double c) {  // camera.rb:153-156 + byte truncation
-  double x = c * 256.0;
-  double m = (255.0 < x) ? 255.0 : x;  // [x, 255].min
-  if (!(m > 0)) return 0;
-  return (uint8_t)(int)m;
-}
+using rtrb::write_pixel;
 
 __device__ __forceinline__ bool slot_to_xy(const FrameParams& P, uint32_t slot, int& x, int& y) {
-  uint32_t k = slot / RTRB_SUPER_PIXELS, q = slot % RTRB_SUPER_PIXELS;
-  int tile = P.tiles[k];
-  int qx, qy;
-  rtrb_morton_decode(q, &qx, &qy);
-  x = (tile % P.stx_count) * RTRB_SUPER + qx;
-  y = (tile / P.stx_count) * RTRB_SUPER + qy;
-  return x >= P.x0 && x < P.x1 && y >= P.y0 && y < P.y1;
-}
-
-__device__ __forceinline__ void write_pixel(const FrameParams& P, int x, int y, double r, double g, double b) {
-  size_t px = (size_t)y * P.width + x;
-  if (P.rgb) { P.rgb[px * 3 + 0] = r; P.rgb[px * 3 + 1] = g; P.rgb[px * 3 + 2] = b; }
-  uchar4 q = make_uchar4(quantise(r), quantise(g), quantise(b), 255);
-  reinterpret_cast<uchar4*>(P.rgba)[px] = q;
+  return rtrb::decode_pixel(P, slot, x, y);
 }
 
 // mean of the pre samples in order, then the variance test (camera.rb:72-87)
@@ -512,6 +495,8 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.counters = r->counters.p; P.status = r->status.p; P.first_bad = r->counters.p + RTRB_CNT_N;
   P.extra_count = r->status.p + 2; P.extra_list = r->extra_list.p; P.extra_samples = r->extra_samples.p;
   P.count_detail = opts.count_detail;
+  // a single sample with a positive threshold can never take the adaptive branch (variance == 0)
+  P.fuse_resolve = (S == 1 && cam->variant_threshold > 0) ? 1 : 0;
 
   const bool strict = opts.precision == RTRB_PREC_STRICT;
   CUDA_TRY(cudaEventRecord(r->ev0, stream));
@@ -529,10 +514,12 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     CUDA_TRY(strict ? rtrb_launch_trace_pre_strict(P, stack_need, stream) : rtrb_launch_trace_pre_fast(P, stack_need, stream));
     CUDA_TRY(cudaEventRecord(r->evt1, stream));
     g_launches++;
-    resolve_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, stream>>>(P);
-    CUDA_TRY(cudaGetLastError());
-    g_launches++;
-    if (E > 0) {
+    if (!P.fuse_resolve) {
+      resolve_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, stream>>>(P);
+      CUDA_TRY(cudaGetLastError());
+      g_launches++;
+    }
+    if (E > 0 && !P.fuse_resolve) {
       CUDA_TRY(strict ? rtrb_launch_trace_extra_strict(P, stack_need, stream) : rtrb_launch_trace_extra_fast(P, stack_need, stream));
       g_launches++;
       resolve_extra_kernel<<<296, 256, 0, stream>>>(P);

@@ -452,6 +452,21 @@ __device__ __forceinline__ void lens_ray(const FrameParams& P, int x, int y, dou
   rd = target - aperture;
 }
 
+// array_to_color (camera.rb:153-156) + the byte truncation of PNG::Color.new
+__device__ __forceinline__ uint8_t quantise_u8(double c) {
+  double x = c * 256.0;
+  double m = (255.0 < x) ? 255.0 : x;  // [x, 255].min
+  if (!(m > 0)) return 0;
+  return (uint8_t)(int)m;
+}
+// render_at's result for pixel (x, y): row = y, column = x (camera.rb:98,105)
+__device__ __forceinline__ void write_pixel(const FrameParams& P, int x, int y, double r, double g, double b) {
+  size_t px = (size_t)y * P.width + x;
+  if (P.rgb) { P.rgb[px * 3 + 0] = r; P.rgb[px * 3 + 1] = g; P.rgb[px * 3 + 2] = b; }
+  uchar4 q = make_uchar4(quantise_u8(r), quantise_u8(g), quantise_u8(b), 255);
+  reinterpret_cast<uchar4*>(P.rgba)[px] = q;
+}
+
 // Decodes work item -> (tile slot k, in-tile q, x, y); returns false when the pixel is outside the window.
 __device__ __forceinline__ bool decode_pixel(const FrameParams& P, uint32_t slot, int& x, int& y) {
   uint32_t k = slot / RTRB_SUPER_PIXELS, q = slot % RTRB_SUPER_PIXELS;
@@ -535,8 +550,13 @@ __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
       int ph;
       d3 col = trace_dispatch<MAXS, FAST>(P, ro, rd, pixel, j, ctx, &ph);
       RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
-      double* out = P.samples + w * 3ull;
-      out[0] = col.x; out[1] = col.y; out[2] = col.z;
+      if (P.fuse_resolve) {
+        // one sample, positive threshold: mean = s / 1.0 = s and variance = 0 < threshold (camera.rb:80-87)
+        write_pixel(P, x, y, col.x, col.y, col.z);
+      } else {
+        double* out = P.samples + w * 3ull;
+        out[0] = col.x; out[1] = col.y; out[2] = col.z;
+      }
       if (j == 0 && P.hit) P.hit[(size_t)y * P.width + x] = ph;
     }
   }

@@ -6,13 +6,16 @@
 namespace {
 
 constexpr int kBlock = 128;
+#ifndef RTRB_FAST_MIN_BLOCKS
+#define RTRB_FAST_MIN_BLOCKS 4
+#endif
 
 template <int MAXS, bool DETAIL>
-__global__ void __launch_bounds__(kBlock) trace_pre_fast_kernel(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kBlock, RTRB_FAST_MIN_BLOCKS) trace_pre_fast_kernel(const __grid_constant__ FrameParams P) {
   rtrb::trace_pre_body<MAXS, DETAIL, true>(P);
 }
 template <int MAXS, bool DETAIL>
-__global__ void __launch_bounds__(kBlock) trace_extra_fast_kernel(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kBlock, RTRB_FAST_MIN_BLOCKS) trace_extra_fast_kernel(const __grid_constant__ FrameParams P) {
   rtrb::trace_extra_body<MAXS, DETAIL, true>(P);
 }
 

@@ -3,18 +3,22 @@
 // Every per-object decision of the reference (does object i win World#intersect, does object i
 // contribute to lit_area, does a light match the highlight test) is first bounded in FP32 with a
 // rigorous error margin; only the objects the filter cannot exclude are re-evaluated with the
-// STRICT FP64 functions of rtrb_trace.cuh, in world_objects order.  Objects the filter excludes
-// contribute exactly what the reference computes for them (no hit / cover 0 / no match), so the
-// frame is bit-identical to STRICT; the filter only removes FP64 work (DESIGN.md "FAST64").
+// STRICT FP64 functions of rtrb_trace.cuh.  Objects the filter excludes contribute exactly what the
+// reference computes for them (no hit / cover 0 / no match), so the frame is bit-identical to
+// STRICT; the filter only removes FP64 work (DESIGN.md "FAST64", with the error-bound derivation).
 //
-// Compiled with -fmad=false as well: the exact parts must not contract, the FP32 filter uses
+// Further exact-preserving economies, each justified where it is made:
+//   * FP64 ray normalisation (1 sqrt + 3 div) is deferred until an exact sphere test needs it;
+//   * children that cannot survive the cut at ray_tracer.rb:52 are not computed;
+//   * divisions by exactly 1.0 (one light) are skipped; the attenuation cut avoids its sqrt
+//     outside a narrow band around the threshold.
+//
+// Compiled with -fmad=false as well: the exact parts must not contract; the FP32 filter uses
 // explicit fmaf().
 #pragma once
 #include "rtrb_trace.cuh"
 
 namespace rtrb {
-
-#define RTRB_CMAX 8  // candidates kept per query before falling back to the exact scan
 
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
@@ -26,30 +30,49 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-
-// A ray as the FP32 filter sees it: origin, UNIT direction, and E = 64 * 2^-24 * (M_scene + |O|_inf),
-// an absolute bound on the FP32 error of every length the filter forms (derivation in DESIGN.md).
-struct CullRay {
-  float ox, oy, oz, dx, dy, dz, E;
-};
-__device__ __forceinline__ CullRay make_cull_ray(const FrameParams& P, d3 o, d3 dn) {
-  CullRay r;
-  r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
-  r.dx = (float)dn.x; r.dy = (float)dn.y; r.dz = (float)dn.z;
-  float m = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
-  r.E = 3.8146973e-6f * (P.m_scene + m);  // 64 * 2^-24
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 
-// Sphere filter. Returns 0 = certainly no hit, 1 = possible hit (lo valid), 2 = certain hit (lo, hi valid).
-// lo/hi bound Ray#distance(intersection) of Sphere#intersect (sphere.rb:60-85).
-__device__ __forceinline__ int cull_sphere(const float4 s, const CullRay& r, float& lo, float& hi) {
+// A ray as the FP32 filter sees it: origin, direction normalised IN FP32 (|d| = 1 +- 4 eps), and
+// E = 96 * 2^-24 * (M_scene + |O|_inf): an absolute bound on the FP32 error of every length the
+// sphere filter forms (DESIGN.md derives <= 45 eps M; 96 leaves slack for the approximate MUFU ops).
+struct CullRay {
+  float ox, oy, oz, dx, dy, dz, E, mo;
+};
+__device__ __forceinline__ CullRay make_cull_ray(const FrameParams& P, d3 o, d3 d) {
+  CullRay r;
+  r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
+  const float fx = (float)d.x, fy = (float)d.y, fz = (float)d.z;
+  const float inv = rsqrt_approx(fmaf(fz, fz, fmaf(fy, fy, fx * fx)));
+  r.dx = fx * inv; r.dy = fy * inv; r.dz = fz * inv;
+  r.mo = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
+  r.E = 5.7220459e-6f * (P.m_scene + r.mo);  // 96 * 2^-24
+  return r;
+}
+
+// Hot reject test of the sphere filter: true when the ray's LINE certainly passes farther than R from
+// the centre.  !(m2 > ...) keeps NaNs as survivors.
+__device__ __forceinline__ bool sphere_line_misses(const float4 s, const CullRay& r) {
   const float ocx = s.x - r.ox, ocy = s.y - r.oy, ocz = s.z - r.oz;
   const float b = fmaf(ocz, r.dz, fmaf(ocy, r.dy, ocx * r.dx));
   const float qx = fmaf(-b, r.dx, ocx), qy = fmaf(-b, r.dy, ocy), qz = fmaf(-b, r.dz, ocz);
   const float m2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
   const float Rp = s.w + r.E;
-  if (m2 > Rp * Rp) return 0;  // the line passes the centre farther than R (+ margin)
+  return m2 > Rp * Rp;
+}
+
+// Full sphere classification (survivors only). 0 = certainly no hit, 1 = possible hit (lo valid),
+// 2 = certain hit (lo, hi valid).  lo/hi bound Ray#distance(intersection) of Sphere#intersect.
+__device__ __forceinline__ int classify_sphere(const float4 s, const CullRay& r, float& lo, float& hi) {
+  const float ocx = s.x - r.ox, ocy = s.y - r.oy, ocz = s.z - r.oz;
+  const float b = fmaf(ocz, r.dz, fmaf(ocy, r.dy, ocx * r.dx));
+  const float qx = fmaf(-b, r.dx, ocx), qy = fmaf(-b, r.dy, ocy), qz = fmaf(-b, r.dz, ocz);
+  const float m2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
+  const float Rp = s.w + r.E;
+  if (m2 > Rp * Rp) return 0;
   const float oc2 = fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx));
   const float Rm = fmaxf(s.w - r.E, 0.0f);
   const bool outside = oc2 > Rp * Rp;
@@ -79,20 +102,20 @@ __device__ __forceinline__ int cull_sphere(const float4 s, const CullRay& r, flo
 }
 
 // Plane filter, same contract; a = (n, |n|_1), p = (P, |P|_inf).  Plane#intersect (plane.rb:38-51).
-__device__ __forceinline__ int cull_plane(const float4 a, const float4 p, const CullRay& r, float& lo, float& hi) {
+__device__ __forceinline__ int classify_plane(const float4 a, const float4 p, const CullRay& r, float& lo, float& hi) {
   const float eps = 5.9604645e-8f;  // 2^-24
   const float den = fmaf(a.z, r.dz, fmaf(a.y, r.dy, a.x * r.dx));
   const float rx = p.x - r.ox, ry = p.y - r.oy, rz = p.z - r.oz;
   const float num = fmaf(rz, a.z, fmaf(ry, a.y, rx * a.x));
-  const float mo = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
-  const float e_num = 16.0f * eps * a.w * (p.w + mo);
-  const float e_den = 8.0f * eps * a.w;
+  const float e_num = 16.0f * eps * a.w * (p.w + r.mo);
+  const float e_den = 16.0f * eps * a.w;
   const float aden = fabsf(den);
-  if (!(aden > 16.0f * e_den)) { lo = 0.0f; hi = 0.0f; return 1; }  // grazing (or NaN): exact test decides
+  lo = 0.0f; hi = 0.0f;
+  if (!(aden > 16.0f * e_den)) return 1;  // grazing (or NaN): the exact test decides
   const float inv = rcp_approx(den);
   const float t = num * inv;
   // |den_true| >= 15/16 |den| here, hence the 1.1
-  const float e_t = (e_num + fabsf(t) * e_den) * fabsf(inv) * 1.1f + 4.0f * eps * fabsf(t);
+  const float e_t = (e_num + fabsf(t) * e_den) * fabsf(inv) * 1.1f + 8.0f * eps * fabsf(t);
   if (t + e_t < 0.0f) return 0;
   lo = fmaxf(t - e_t, 0.0f);
   hi = t + e_t;
@@ -100,74 +123,28 @@ __device__ __forceinline__ int cull_plane(const float4 a, const float4 p, const 
   return (t - e_t > 0.0f) ? 2 : 1;
 }
 
-struct CandList {
+// Up to 8 survivor slots of 16 bits each, kept in two registers (no local-memory array).
+struct Pack8 {
+  unsigned long long a, b;
   int n;
-  bool overflow;
-  int idx[RTRB_CMAX];
-  float lo[RTRB_CMAX];
-  __device__ __forceinline__ void clear() { n = 0; overflow = false; }
-  __device__ __forceinline__ void push(int i, float l) {
-    if (n < RTRB_CMAX) { idx[n] = i; lo[n] = l; n++; }
-    else overflow = true;
+  __device__ __forceinline__ void clear() { a = 0ull; b = 0ull; n = 0; }
+  __device__ __forceinline__ void push(uint32_t v) {
+    if (n < 4) a |= (unsigned long long)v << (16 * n);
+    else if (n < 8) b |= (unsigned long long)v << (16 * (n - 4));
+    n++;
   }
-  // ascending world_objects index (insertion sort; n <= 8)
-  __device__ __forceinline__ void sort_by_index() {
-    for (int a = 1; a < n; ++a) {
-      int ki = idx[a]; float kl = lo[a];
-      int b = a - 1;
-      while (b >= 0 && idx[b] > ki) { idx[b + 1] = idx[b]; lo[b + 1] = lo[b]; --b; }
-      idx[b + 1] = ki; lo[b + 1] = kl;
-    }
+  __device__ __forceinline__ bool overflow() const { return n > 8; }
+  __device__ __forceinline__ uint32_t get(int i) const {
+    return (uint32_t)(((i < 4) ? (a >> (16 * i)) : (b >> (16 * (i - 4)))) & 0xffffull);
   }
 };
 
-// World#intersect (world.rb:37-59) = FP32 filter over every object + exact test of the survivors.
-__device__ __forceinline__ int closest_hit_fast(const FrameParams& P, d3 o, d3 d, double d_r, d3 dn, HitRec& bh,
-                                                ThreadCtx& ctx) {
-  const CullRay r = make_cull_ray(P, o, dn);
-  CandList cl;
-  cl.clear();
-  float best_hi = P.max_distance_f;  // no object at or beyond max_distance can win (initial nearest_dis)
-  for (int k = 0; k < P.n_sph; ++k) {
-    const float4 s = __ldg(&P.cull_sph[k]);
-    float lo, hi;
-    const int kind = cull_sphere(s, r, lo, hi);
-    if (kind != 0 && lo <= best_hi) {
-      cl.push(P.sph_index[k], lo);
-      if (kind == 2) best_hi = fminf(best_hi, hi);
-    }
-  }
-  for (int k = 0; k < P.n_pl; ++k) {
-    const float4 a = __ldg(&P.cull_pl[2 * k]), p = __ldg(&P.cull_pl[2 * k + 1]);
-    float lo, hi;
-    const int kind = cull_plane(a, p, r, lo, hi);
-    if (kind != 0 && lo <= best_hi) {
-      cl.push(P.pl_index[k], lo);
-      if (kind == 2) best_hi = fminf(best_hi, hi);
-    }
-  }
+// The reference's own scan (world.rb:44-57); used when the filter keeps more survivors than fit.
+static __device__ __noinline__ int closest_hit_scan(const FrameParams& P, d3 o, d3 d, HitRec& bh, ThreadCtx& ctx) {
+  const double d_r = norm(d);
+  const d3 dn = mk(d.x / d_r, d.y / d_r, d.z / d_r);
   double best = P.max_distance;
   int best_i = -1;
-  if (!cl.overflow) {
-    // exact evaluation of the survivors; (distance, index) lexicographic == strict `<` in index order
-    for (int c = 0; c < cl.n; ++c) {
-      if (!(cl.lo[c] <= best_hi)) continue;
-      const int i = cl.idx[c];
-      const DevGeom g = P.geom[i];
-      HitRec h;
-      bool ok;
-      double den;
-      if (g.type == RTRB_OBJ_SPHERE) ok = sphere_intersect(g, o, d, d_r, dn, h);
-      else ok = plane_intersect(g, o, d, h, den);
-      RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-      if (ok) {
-        const double new_dis = norm(o - h.p);
-        if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; bh = h; }
-      }
-    }
-    return best_i;
-  }
-  // more survivors than the list holds (rare): the reference's own scan
   for (int i = 0; i < P.n_objects; ++i) {
     const DevGeom g = P.geom[i];
     HitRec h;
@@ -184,41 +161,122 @@ __device__ __forceinline__ int closest_hit_fast(const FrameParams& P, d3 o, d3 d
   return best_i;
 }
 
-// World#lit_area (world.rb:62-69) = filter + exact cover of the survivors, subtracted in index order.
-// An object the probe ray certainly misses (or certainly meets beyond the light) has factor 0, hence
-// cover exactly 0 (sphere.rb:29,45-53 multiply everything by factor; world_object.rb:43-47).
-__device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
-  const CoverRay c = make_cover_ray(target, L);
-  const CullRay r = make_cull_ray(P, target, c.ltn);
-  const float ell = (float)c.lt_r;
-  const float far = ell * 1.00001f + 2.0f * r.E;  // hits farther than the light cannot cover
-  CandList cl;
-  cl.clear();
+// World#intersect (world.rb:37-59) = FP32 filter over every object + exact test of the survivors.
+__device__ __forceinline__ int closest_hit_fast(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
+                                                ThreadCtx& ctx) {
+  Pack8 S;
+  S.clear();
+  if (P.n_sph > 65535) return closest_hit_scan(P, o, d, bh, ctx);
+#pragma unroll 4
   for (int k = 0; k < P.n_sph; ++k) {
     const float4 s = __ldg(&P.cull_sph[k]);
+    if (!sphere_line_misses(s, r)) S.push((uint32_t)k);
+  }
+  if (S.overflow() || P.n_pl > 8) return closest_hit_scan(P, o, d, bh, ctx);
+  // pass 1: the smallest certain upper bound; nothing at or beyond max_distance can win (world.rb:39)
+  float best_hi = P.max_distance_f;
+  for (int c = 0; c < S.n; ++c) {
     float lo, hi;
-    const int kind = cull_sphere(s, r, lo, hi);
-    if (kind != 0 && !(lo > far)) cl.push(P.sph_index[k], lo);
+    if (classify_sphere(__ldg(&P.cull_sph[S.get(c)]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
   }
   for (int k = 0; k < P.n_pl; ++k) {
-    const float4 a = __ldg(&P.cull_pl[2 * k]), p = __ldg(&P.cull_pl[2 * k + 1]);
     float lo, hi;
-    const int kind = cull_plane(a, p, r, lo, hi);
-    if (kind != 0 && !(lo > far)) cl.push(P.pl_index[k], lo);
+    if (classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
   }
-  double total = 1;
-  if (!cl.overflow) {
-    cl.sort_by_index();
-    for (int k = 0; k < cl.n; ++k) {
-      const DevGeom g = P.geom[cl.idx[k]];
-      RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-      total -= cover_object_exact(g, c, L.radius, ctx);
+  // pass 2: exact FP64 evaluation of whatever can still win; (distance, index) lexicographic order
+  // reproduces the strict `<` scan in world_objects order.
+  double best = P.max_distance;
+  int best_i = -1;
+  bool have_dn = false;
+  double d_r = 0;
+  d3 dn = mk(0, 0, 0);
+  for (int c = 0; c < S.n; ++c) {
+    const uint32_t k = S.get(c);
+    float lo, hi;
+    const int kind = classify_sphere(__ldg(&P.cull_sph[k]), r, lo, hi);
+    if (kind == 0 || !(lo <= best_hi)) continue;
+    if (!have_dn) { d_r = norm(d); dn = mk(d.x / d_r, d.y / d_r, d.z / d_r); have_dn = true; }
+    const int i = P.sph_index[k];
+    const DevGeom g = P.geom[i];
+    HitRec h;
+    RTRB_COUNT(ctx, RTRB_CNT_EXACT);
+    if (sphere_intersect(g, o, d, d_r, dn, h)) {
+      const double new_dis = norm(o - h.p);
+      if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; bh = h; }
     }
-  } else {
-    for (int i = 0; i < P.n_objects; ++i) {
-      const DevGeom g = P.geom[i];
+  }
+  for (int k = 0; k < P.n_pl; ++k) {
+    float lo, hi;
+    const int kind = classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi);
+    if (kind == 0 || !(lo <= best_hi)) continue;
+    const int i = P.pl_index[k];
+    const DevGeom g = P.geom[i];
+    HitRec h;
+    double den;
+    RTRB_COUNT(ctx, RTRB_CNT_EXACT);
+    if (plane_intersect(g, o, d, h, den)) {
+      const double new_dis = norm(o - h.p);
+      if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; bh = h; }
+    }
+  }
+  return best_i;
+}
+
+// World#lit_area (world.rb:62-69) = filter + exact cover of the survivors, subtracted in index order.
+// An object the probe ray certainly misses (or certainly meets beyond the light) has factor 0, hence
+// cover exactly 0 (sphere.rb:29,45-53 multiply everything by factor; world_object.rb:43-47), and
+// total - 0 == total, so skipping it leaves the running difference bit-identical.
+__device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
+  CoverRay c;
+  c.target = target;
+  c.lp = mk(L.px, L.py, L.pz);
+  c.lt = c.lp - target;
+  c.tl = target - c.lp;
+  c.lt_r = 0; c.ltn = mk(0, 0, 0);
+  const CullRay r = make_cull_ray(P, target, c.lt);
+  float far;  // hits farther than the light cannot cover: factor needs dot(hit - L, T - L) > 0
+  {
+    const float lx = (float)c.lt.x, ly = (float)c.lt.y, lz = (float)c.lt.z;
+    far = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) * 1.00001f + 2.0f * r.E;
+  }
+  if (P.n_sph > 65535 || P.n_pl > 65535) return lit_area(P, target, L, ctx);
+  Pack8 S, Q;
+  S.clear();
+  Q.clear();
+#pragma unroll 4
+  for (int k = 0; k < P.n_sph; ++k) {
+    const float4 s = __ldg(&P.cull_sph[k]);
+    if (!sphere_line_misses(s, r)) S.push((uint32_t)k);
+  }
+  for (int k = 0; k < P.n_pl; ++k) {
+    float lo, hi;
+    const int kind = classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi);
+    if (kind != 0 && !(lo > far)) Q.push((uint32_t)k);
+  }
+  if (S.overflow() || Q.overflow()) return lit_area(P, target, L, ctx);
+  double total = 1;
+  bool have_n = false;
+  int cs = 0, cq = 0;
+  // merge the two survivor lists (each ascending in world_objects index) so covers subtract in order
+  while (cs < S.n || cq < Q.n) {
+    const int is = cs < S.n ? P.sph_index[S.get(cs)] : 0x7fffffff;
+    const int iq = cq < Q.n ? P.pl_index[Q.get(cq)] : 0x7fffffff;
+    if (is < iq) {
+      const uint32_t k = S.get(cs++);
+      float lo, hi;
+      const int kind = classify_sphere(__ldg(&P.cull_sph[k]), r, lo, hi);
+      if (kind == 0 || lo > far) continue;
+      if (!have_n) {
+        c.lt_r = norm(c.lt);
+        c.ltn = mk(c.lt.x / c.lt_r, c.lt.y / c.lt_r, c.lt.z / c.lt_r);
+        have_n = true;
+      }
       RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-      total -= cover_object_exact(g, c, L.radius, ctx);
+      total -= cover_object_exact(P.geom[is], c, L.radius, ctx);
+    } else {
+      cq++;
+      RTRB_COUNT(ctx, RTRB_CNT_EXACT);
+      total -= cover_object_exact(P.geom[iq], c, L.radius, ctx);
     }
   }
   return fmax(total, 0.0);
@@ -232,11 +290,10 @@ __device__ __forceinline__ bool highlight_match_fast(const DevLight& L, const De
   const float ax = F.px - r.ox, ay = F.py - r.oy, az = F.pz - r.oz;
   const float ret = fmaf(az, r.dz, fmaf(ay, r.dy, ax * r.dx));
   const float a2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
-  const float mo = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
-  const float ea = 8.0f * eps * (F.pmax + mo);
+  const float ea = 8.0f * eps * (F.pmax + r.mo);
   const float c2 = ret * ret * rcp_approx(a2);
-  const float rho = 8.0f * (ea * rsqrtf(a2) + 8.0f * eps);  // absolute error bound on |cos| (<= 1)
-  const float tol = fmaf(rho, rho, 2.0f * rho);              // ... hence on cos^2
+  const float rho = 8.0f * (ea * rsqrt_approx(a2) + 8.0f * eps);  // absolute error bound on |cos| (<= 1)
+  const float tol = fmaf(rho, rho, 2.0f * rho);                    // ... hence on cos^2
   if (F.mode == 1 && rho < 0.25f) {
     if (c2 - tol > F.cos2_thr) return true;
     if (c2 + tol < F.cos2_thr) return false;
@@ -246,6 +303,14 @@ __device__ __forceinline__ bool highlight_match_fast(const DevLight& L, const De
   double ct = vcos(d, a, ctx);
   double ang = rb_acos(ct, ctx);
   return ang < L.hl_threshold;
+}
+
+// `attenuation.r < 0.0001` (ray_tracer.rb:52) without the square root outside a narrow band.
+__device__ __forceinline__ bool attenuation_dead(d3 att) {
+  const double s2 = sumsq(att);
+  if (s2 > 1.0001e-8) return false;
+  if (s2 < 0.9999e-8) return true;
+  return sqrt(s2) < 0.0001;
 }
 
 // RayTracer#trace_sync, FAST64 evaluation.  Same contract as trace_sample<MAXS> in rtrb_trace.cuh.
@@ -269,15 +334,13 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
     const bool is_first = first;
     first = false;
     const d3 o = mk(it.ox, it.oy, it.oz), d = mk(it.dx, it.dy, it.dz), att = mk(it.ax, it.ay, it.az);
-    if (it.depth <= 0 || norm(att) < 0.0001) continue;  // rt_map :52
+    if (it.depth <= 0 || attenuation_dead(att)) continue;  // rt_map :52
     ctx.rays++;
 
-    const double d_r = norm(d);
-    const d3 dn = mk(d.x / d_r, d.y / d_r, d.z / d_r);
+    const CullRay r = make_cull_ray(P, o, d);
 
     // ---- World#high_lights ----
     {
-      const CullRay r = make_cull_ray(P, o, dn);
       unsigned long long hl_mask = 0ull;
       int hl_n = 0;
       for (int l = 0; l < P.n_lights; ++l)
@@ -285,7 +348,8 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
       if (hl_n > 0) {
         for (int l = 0; l < P.n_lights; ++l) {
           if (!((hl_mask >> l) & 1ull)) continue;
-          d3 c = (att * ld3(P.lights[l].color_hl)) / (double)hl_n;
+          d3 c = att * ld3(P.lights[l].color_hl);
+          if (hl_n != 1) c = c / (double)hl_n;  // x / 1.0 == x
           sum = sum + c;
           if (sum.x > 1 || sum.y > 1 || sum.z > 1) ctx.status |= RTRB_ST_COLOR_GT_1;
         }
@@ -297,7 +361,7 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
 
     // ---- World#intersect ----
     HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false;
-    const int best_i = closest_hit_fast(P, o, d, d_r, dn, bh, ctx);
+    const int best_i = closest_hit_fast(P, o, d, r, bh, ctx);
     if (best_i < 0) continue;
     if (is_first) *primary_hit = best_i;
     RTRB_COUNT(ctx, RTRB_CNT_HITS);
@@ -329,7 +393,7 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
     // A child with trace_depth - 1 <= 0, or whose attenuation norm is certainly < 1e-4, is popped and
     // dropped by the reference without any observable effect; skipping its direction math changes
     // nothing except in the one case where that math would RAISE (normalize of an exactly zero
-    // reflection + d, world_object.rb:136) — detected below by a cheap necessary condition.
+    // reflection + d, world_object.rb:136, or a zero normal) — caught by a cheap necessary condition.
     const d3 a_refl = att * ld3(M.refl), a_refr = att * ld3(M.refr);
     const bool depth_ok = it.depth - 1 > 0;
     const bool refl_alive = depth_ok && !(sumsq(a_refl) < 0.99e-8);
@@ -338,6 +402,7 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
     const bool near_normal = !(dn_dot * dn_dot < (1.0 - 1e-9) * (sumsq(d) * sumsq(n)));  // possible raise site
     if (refl_alive || refr_alive || near_normal) {
       if (sp + 2 > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; continue; }
+      const double d_r = norm(d);
       const double cos_theta = vcos(d, -n, ctx);  // == vcos(d, n): both square the dot product
       const d3 refl_dir = normalize(nn * (2 * cos_theta * d_r) + d, ctx);
       if (refl_alive || near_normal) {
@@ -375,7 +440,9 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
       ctx.shadow++;
       const double area = lit_area_fast(P, shade_from, L, ctx);
       if (area > 0) {
-        d3 lc = ld3(L.color) * (rb_pow(area, P.soft_shadow_exponent) / (double)P.n_lights);
+        double w = rb_pow(area, P.soft_shadow_exponent);
+        if (P.n_lights != 1) w = w / (double)P.n_lights;  // x / 1.0 == x
+        d3 lc = ld3(L.color) * w;
         d3 lv = normalize(mk(L.px, L.py, L.pz) - bh.p, ctx);
         double ldn = dot(lv, nn);
         if (ldn > 1) ldn = 1.0; else if (ldn < 0) ldn = 0.0;
@@ -390,7 +457,7 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
         const d3 a2 = att * att_pt;
         const bool mc_alive = depth_ok && !(sumsq(a2) < 0.99e-8);
         const d3 vv = a_vertical_vector(n, ctx);
-        if (mc_alive || norm(vv) == 0) {
+        if (mc_alive || sumsq(vv) == 0) {
           const d3 leftv = normalize(vv, ctx);
           const d3 upv = cross(nn, leftv);
           for (int m = 0; m < P.mc; ++m) {
@@ -411,7 +478,7 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
     } else {
       RTRB_COUNT(ctx, RTRB_CNT_LOCAL);
       if (ctx.detail) ctx.c[RTRB_CNT_LIT] += n_lit;
-      contrib = contrib / (double)n_lit;
+      if (n_lit != 1) contrib = contrib / (double)n_lit;  // x / 1.0 == x
       d3 filter = mk(1.0, 1.0, 1.0);
       if (M.tex != nullptr) {
         double u, v;

@@ -103,7 +103,7 @@ struct FrameParams {
   uint32_t* extra_list;        // [n_tiles*1024] pixel slots (tile k * 1024 + q)
   double* extra_samples;       // [extra][max-pre][3]
   int32_t count_detail;
-  int32_t pad;
+  int32_t fuse_resolve;        // pre == max == 1 style frames: the trace kernel writes the pixel itself
 };
 
 enum {
