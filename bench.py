@@ -173,7 +173,11 @@ def run_ours(args, rank, local_rank, world_size):
             torch.cuda.synchronize()
 
     # ---- untimed: per-frame work of this rank (counters) and the FMA issue peaks ----
-    st_detail, _ = r.render_device(cd, opts(True))
+    # the algorithmic (brute-force) operation counts come from the STRICT kernel's detailed counters:
+    # FAST64 produces the same frame with fewer executed tests, which must not shrink the numerator
+    so = opts(True)
+    so.precision = PREC_STRICT
+    st_detail, _ = r.render_device(cd, so)
     flops_frame = algorithmic_flops(st_detail)
     rays_frame = st_detail["rays"] + st_detail["shadow_queries"]
     peak64 = measure_fma_peak(local_rank, True) if rank == 0 else 0.0

@@ -131,7 +131,8 @@ typedef struct rtrb_render_opts {
    * A column strip is exactly render_fork's child_work (camera.rb:53-65). */
   int32_t x0, y0, x1, y1;
   /* image-tile partition (replaces fork_jobs row farming): this call renders the 32x32-pixel
-   * super-tiles b with b % tile_world == tile_rank. tile_world <= 1 = everything. */
+   * super-tiles number tile_rank, tile_rank + tile_world, ... of the window (row-major order; see
+   * rtrb_tile_partition). tile_world <= 1 = everything. */
   int32_t tile_rank, tile_world;
   int32_t count_detail; /* 1 = fill every rtrb_stats counter (slower); 0 = rays/shadow/samples only */
   int32_t reserved0;
@@ -205,6 +206,13 @@ int rtrb_ipc_close(int device, void* ptr);
 int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_desc* cam,
                       const rtrb_render_opts* opts, uint8_t* rgba, double* rgb_or_null,
                       int32_t* hit_or_null, rtrb_stats* stats_out);
+
+/* Pure host helper (no GPU): the 32x32-pixel super-tiles of a width x height frame (optionally
+ * clipped to window {x0,y0,x1,y1}, NULL = whole frame) that tile_rank renders out of tile_world,
+ * as global ids ty * ceil(width/32) + tx in ascending order.  count_out receives the number of
+ * tiles even when it exceeds capacity.  This is the partition rtrb_render_device applies. */
+int rtrb_tile_partition(int width, int height, const int32_t* window_or_null, int tile_rank, int tile_world,
+                        int32_t* tiles_out, int capacity, int* count_out);
 
 /* -- measurement helpers ---------------------------------------------------------------------- */
 /* Dependent-free FMA issue microbenchmark on `device`: the roofline denominator SURVEY.md 8d asks

@@ -11,7 +11,7 @@ from .configurable_object import ConfigurableObject
 from .lights import Light, SpotLight
 from .objects import Plane, Sphere, WorldObject
 from .renderer import (Frame, Renderer, device_count, ipc_close, ipc_open, make_opts, measure_fma_peak,
-                       render_multi)
+                       render_multi, tile_partition)
 from .texture import Texture
 from .vec3 import Vec3
 from .world import World
@@ -19,6 +19,6 @@ from .world import World
 __all__ = [
     "Camera", "World", "Sphere", "Plane", "WorldObject", "Light", "SpotLight", "Texture", "Vec3",
     "ConfigurableObject", "Renderer", "Frame", "make_opts", "render_multi", "measure_fma_peak",
-    "device_count", "ipc_open", "ipc_close", "write_png",
+    "device_count", "ipc_open", "ipc_close", "write_png", "tile_partition",
     "PREC_STRICT", "PREC_FAST64", "PREC_DEFAULT", "RNG_CTR", "RNG_MT",
 ]

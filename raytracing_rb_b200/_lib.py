@@ -13,7 +13,7 @@ EXPORTS = (
     "rtrb_renderer_create", "rtrb_renderer_destroy",
     "rtrb_render_device", "rtrb_download", "rtrb_render",
     "rtrb_framebuffer_device_ptr", "rtrb_framebuffer_ipc_export", "rtrb_ipc_open", "rtrb_ipc_close",
-    "rtrb_render_multi", "rtrb_measure_fma_peak", "rtrb_launch_count",
+    "rtrb_render_multi", "rtrb_tile_partition", "rtrb_measure_fma_peak", "rtrb_launch_count",
 )
 
 _lib = None
@@ -50,6 +50,7 @@ def lib():
     L.rtrb_ipc_close.argtypes = [C.c_int, C.c_void_p]
     L.rtrb_render_multi.argtypes = [P(C.c_void_p), C.c_int, P(_abi.CameraDesc), P(_abi.RenderOpts), C.c_void_p,
                                     C.c_void_p, C.c_void_p, P(_abi.Stats)]
+    L.rtrb_tile_partition.argtypes = [C.c_int, C.c_int, P(C.c_int32), C.c_int, C.c_int, P(C.c_int32), C.c_int, P(C.c_int)]
     L.rtrb_measure_fma_peak.argtypes = [C.c_int, C.c_int, P(C.c_double)]
     L.rtrb_launch_count.restype = C.c_uint64
     for name in EXPORTS:

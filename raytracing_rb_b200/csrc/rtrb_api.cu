@@ -387,6 +387,16 @@ void bake_camera(FrameParams& P, const rtrb_camera_desc* c) {
   P.trace_depth = c->trace_depth; P.mc = c->monte_carlo_diffusion_times;
 }
 
+void enumerate_tiles(int W, int x0, int y0, int x1, int y1, int rank, int world, std::vector<int32_t>& out) {
+  const int stx_count = (W + RTRB_SUPER - 1) / RTRB_SUPER;
+  out.clear();
+  // deal the window's super-tiles round-robin in row-major order: shares differ by at most one tile
+  int i = 0;
+  for (int ty = y0 / RTRB_SUPER; ty <= (y1 - 1) / RTRB_SUPER; ++ty)
+    for (int tx = x0 / RTRB_SUPER; tx <= (x1 - 1) / RTRB_SUPER; ++tx, ++i)
+      if (i % world == rank) out.push_back(ty * stx_count + tx);
+}
+
 struct FrameTargets {  // where this renderer writes (own buffers, or rank 0's through a peer mapping)
   uint8_t* rgba = nullptr;
   double* rgb = nullptr;
@@ -454,12 +464,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   const int stx_count = (W + RTRB_SUPER - 1) / RTRB_SUPER;
   int key[8] = {W, H, x0, y0, x1, y1, rank, world};
   if (memcmp(key, r->tiles_key, sizeof(key)) != 0) {
-    r->tiles_host.clear();
-    for (int ty = y0 / RTRB_SUPER; ty <= (y1 - 1) / RTRB_SUPER; ++ty)
-      for (int tx = x0 / RTRB_SUPER; tx <= (x1 - 1) / RTRB_SUPER; ++tx) {
-        int b = ty * stx_count + tx;
-        if (b % world == rank) r->tiles_host.push_back(b);
-      }
+    enumerate_tiles(W, x0, y0, x1, y1, rank, world, r->tiles_host);
     CUDA_TRY(r->tiles.ensure(std::max<size_t>(1, r->tiles_host.size())));
     if (!r->tiles_host.empty())
       CUDA_TRY(cudaMemcpyAsync(r->tiles.p, r->tiles_host.data(), r->tiles_host.size() * sizeof(int32_t),
@@ -811,6 +816,25 @@ int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_
   if (rc) return rc;
   if (worst == RTRB_ERR_RAISED) g_last_error = keep;
   return worst;
+}
+
+int rtrb_tile_partition(int width, int height, const int32_t* window, int tile_rank, int tile_world,
+                        int32_t* tiles_out, int capacity, int* count_out) {
+  if (width <= 0 || height <= 0 || !count_out) return fail(RTRB_ERR_INVALID, "bad argument");
+  int x0 = 0, y0 = 0, x1 = width, y1 = height;
+  if (window && !(window[0] == 0 && window[1] == 0 && window[2] == 0 && window[3] == 0)) {
+    x0 = window[0]; y0 = window[1]; x1 = window[2]; y1 = window[3];
+  }
+  if (x0 < 0 || y0 < 0 || x1 > width || y1 > height || x0 >= x1 || y0 >= y1) return fail(RTRB_ERR_INVALID, "bad window");
+  int world = tile_world <= 1 ? 1 : tile_world;
+  int rank = world == 1 ? 0 : tile_rank;
+  if (rank < 0 || rank >= world) return fail(RTRB_ERR_INVALID, "tile_rank %d outside tile_world %d", rank, world);
+  std::vector<int32_t> t;
+  enumerate_tiles(width, x0, y0, x1, y1, rank, world, t);
+  *count_out = (int)t.size();
+  if (tiles_out)
+    for (int i = 0; i < (int)t.size() && i < capacity; ++i) tiles_out[i] = t[i];
+  return RTRB_OK;
 }
 
 int rtrb_measure_fma_peak(int device, int which, double* tflops_out) {

@@ -129,6 +129,16 @@ def render_multi(renderers, cam, opts=None, want_rgb=True, want_hit=True):
     return Frame(rgba, rgb, hit, st.as_dict(), code)
 
 
+def tile_partition(width, height, tile_rank=0, tile_world=1, window=None):
+    """The super-tile ids (ty * ceil(width/32) + tx) `tile_rank` of `tile_world` renders.  Pure host logic."""
+    win = (C.c_int32 * 4)(*(window or (0, 0, 0, 0)))
+    n = C.c_int()
+    check(lib().rtrb_tile_partition(width, height, win, tile_rank, tile_world, None, 0, C.byref(n)))
+    out = (C.c_int32 * max(1, n.value))()
+    check(lib().rtrb_tile_partition(width, height, win, tile_rank, tile_world, out, n.value, C.byref(n)))
+    return list(out[:n.value])
+
+
 def measure_fma_peak(device=0, fp64=True):
     v = C.c_double()
     check(lib().rtrb_measure_fma_peak(device, 1 if fp64 else 0, C.byref(v)))
