@@ -481,7 +481,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   CUDA_TRY(r->samples.ensure(std::max<size_t>(1, n_slots * S * 3)));
   CUDA_TRY(r->extra_list.ensure(std::max<size_t>(1, n_slots)));
   if (E > 0) CUDA_TRY(r->extra_samples.ensure(n_slots * E * 3));
-  CUDA_TRY(r->counters.ensure(RTRB_CNT_N + 1));
+  CUDA_TRY(r->counters.ensure(RTRB_CNT_N + 3));
   CUDA_TRY(r->status.ensure(4));
 
   FrameParams P;
@@ -498,6 +498,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.n_tiles = n_tiles; P.stx_count = stx_count; P.tiles = r->tiles.p;
   P.samples = r->samples.p; P.rgb = tg.rgb; P.hit = tg.hit; P.rgba = tg.rgba;
   P.counters = r->counters.p; P.status = r->status.p; P.first_bad = r->counters.p + RTRB_CNT_N;
+  P.work_counter = r->counters.p + RTRB_CNT_N + 1;
   P.extra_count = r->status.p + 2; P.extra_list = r->extra_list.p; P.extra_samples = r->extra_samples.p;
   P.count_detail = opts.count_detail;
   // a single sample with a positive threshold can never take the adaptive branch (variance == 0)
@@ -507,6 +508,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   CUDA_TRY(cudaEventRecord(r->ev0, stream));
   CUDA_TRY(cudaMemsetAsync(r->counters.p, 0, RTRB_CNT_N * sizeof(unsigned long long), stream));
   CUDA_TRY(cudaMemsetAsync(r->counters.p + RTRB_CNT_N, 0xff, sizeof(unsigned long long), stream));
+  CUDA_TRY(cudaMemsetAsync(r->counters.p + RTRB_CNT_N + 1, 0, 2 * sizeof(unsigned long long), stream));
   CUDA_TRY(cudaMemsetAsync(r->status.p, 0, 4 * sizeof(uint32_t), stream));
   const bool partial = !(x0 == 0 && y0 == 0 && x1 == W && y1 == H && world == 1);
   if (partial && !tg.no_fill && tg.hit == r->hit.p && tg.hit) {

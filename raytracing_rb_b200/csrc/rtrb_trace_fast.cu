@@ -19,6 +19,11 @@ __global__ void __launch_bounds__(kBlock, RTRB_FAST_MIN_BLOCKS) trace_extra_fast
   rtrb::trace_extra_body<MAXS, DETAIL, true>(P);
 }
 
+// A persistent-thread variant (lanes refetch a new sample when their stack empties) was measured in
+// round 1 and REJECTED: on config 3 the flat grid already runs at 29.1/32 active threads per
+// instruction because neighbouring samples have similar ray trees; refetching mixed unrelated rays
+// into one warp (22.9/32) and ran 1.8x slower (profiles/README.md).
+
 template <int MAXS, bool DETAIL>
 cudaError_t launch_pre(const FrameParams& P, cudaStream_t s) {
   unsigned long long total = (unsigned long long)P.n_tiles * RTRB_SUPER_PIXELS * (unsigned long long)P.pre;

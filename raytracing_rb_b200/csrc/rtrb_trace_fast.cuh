@@ -313,28 +313,16 @@ __device__ __forceinline__ bool attenuation_dead(d3 att) {
   return sqrt(s2) < 0.0001;
 }
 
-// RayTracer#trace_sync, FAST64 evaluation.  Same contract as trace_sample<MAXS> in rtrb_trace.cuh.
+// rt_map (ray_tracer.rb:50-164) for ONE popped work item, FAST64 evaluation: pushes the children
+// onto `stack`, adds the emitted colours to `sum` in emission order.
 template <int MAXS>
-__device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
-                                                ThreadCtx& ctx, int* primary_hit) {
-  StackItem stack[MAXS];
-  stack[0].ox = ro.x; stack[0].oy = ro.y; stack[0].oz = ro.z;
-  stack[0].dx = rd.x; stack[0].dy = rd.y; stack[0].dz = rd.z;
-  stack[0].ax = 1.0; stack[0].ay = 1.0; stack[0].az = 1.0;
-  stack[0].depth = P.trace_depth; stack[0].path = 1u;
-  int sp = 1;
-  d3 sum = mk(0.0, 0.0, 0.0);
-  bool first = true;
+__device__ __forceinline__ void process_item_fast(const FrameParams& P, const StackItem& it, StackItem* stack, int& sp,
+                                                  d3& sum, ThreadCtx& ctx, uint32_t pixel, uint32_t sample,
+                                                  bool is_first, int* primary_hit) {
   const uint32_t K = (uint32_t)(P.mc + 2);
-  *primary_hit = -1;
-
-  while (sp > 0) {
-    if ((uint32_t)sp > ctx.max_stack) ctx.max_stack = (uint32_t)sp;
-    const StackItem it = stack[--sp];
-    const bool is_first = first;
-    first = false;
+  {
     const d3 o = mk(it.ox, it.oy, it.oz), d = mk(it.dx, it.dy, it.dz), att = mk(it.ax, it.ay, it.az);
-    if (it.depth <= 0 || attenuation_dead(att)) continue;  // rt_map :52
+    if (it.depth <= 0 || attenuation_dead(att)) return;  // rt_map :52
     ctx.rays++;
 
     const CullRay r = make_cull_ray(P, o, d);
@@ -347,7 +335,7 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
         if (highlight_match_fast(P.lights[l], P.lights_f[l], o, d, r, ctx)) { hl_mask |= 1ull << l; hl_n++; }
       if (hl_n > 0) {
         for (int l = 0; l < P.n_lights; ++l) {
-          if (!((hl_mask >> l) & 1ull)) continue;
+          if (!((hl_mask >> l) & 1ull)) return;
           d3 c = att * ld3(P.lights[l].color_hl);
           if (hl_n != 1) c = c / (double)hl_n;  // x / 1.0 == x
           sum = sum + c;
@@ -355,14 +343,14 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
         }
         RTRB_COUNT(ctx, RTRB_CNT_HIGHLIGHT);
         if (is_first) *primary_hit = -2;
-        continue;
+        return;
       }
     }
 
     // ---- World#intersect ----
     HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false;
     const int best_i = closest_hit_fast(P, o, d, r, bh, ctx);
-    if (best_i < 0) continue;
+    if (best_i < 0) return;
     if (is_first) *primary_hit = best_i;
     RTRB_COUNT(ctx, RTRB_CNT_HITS);
 
@@ -401,7 +389,7 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
     const double dn_dot = dot(d, n);
     const bool near_normal = !(dn_dot * dn_dot < (1.0 - 1e-9) * (sumsq(d) * sumsq(n)));  // possible raise site
     if (refl_alive || refr_alive || near_normal) {
-      if (sp + 2 > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; continue; }
+      if (sp + 2 > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; return; }
       const double d_r = norm(d);
       const double cos_theta = vcos(d, -n, ctx);  // == vcos(d, n): both square the dot product
       const d3 refl_dir = normalize(nn * (2 * cos_theta * d_r) + d, ctx);
@@ -452,7 +440,7 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
     }
     if (n_lit == 0) {
       if (P.mc > 0) {
-        if (sp + P.mc > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; continue; }
+        if (sp + P.mc > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; return; }
         const d3 att_pt = ld3(M.diffuse) / (double)P.mc;
         const d3 a2 = att * att_pt;
         const bool mc_alive = depth_ok && !(sumsq(a2) < 0.99e-8);
@@ -503,6 +491,27 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
       sum = sum + c;
       if (sum.x > 1 || sum.y > 1 || sum.z > 1) ctx.status |= RTRB_ST_COLOR_GT_1;
     }
+  }
+}
+
+// RayTracer#trace_sync for one sample (non-persistent form; used by tools and kept for reference).
+template <int MAXS>
+__device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
+                                                ThreadCtx& ctx, int* primary_hit) {
+  StackItem stack[MAXS];
+  stack[0].ox = ro.x; stack[0].oy = ro.y; stack[0].oz = ro.z;
+  stack[0].dx = rd.x; stack[0].dy = rd.y; stack[0].dz = rd.z;
+  stack[0].ax = 1.0; stack[0].ay = 1.0; stack[0].az = 1.0;
+  stack[0].depth = P.trace_depth; stack[0].path = 1u;
+  int sp = 1;
+  d3 sum = mk(0.0, 0.0, 0.0);
+  bool first = true;
+  *primary_hit = -1;
+  while (sp > 0) {
+    if ((uint32_t)sp > ctx.max_stack) ctx.max_stack = (uint32_t)sp;
+    const StackItem it = stack[--sp];
+    process_item_fast<MAXS>(P, it, stack, sp, sum, ctx, pixel, sample, first, primary_hit);
+    first = false;
   }
   return sum;
 }

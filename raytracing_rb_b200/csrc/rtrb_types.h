@@ -102,6 +102,7 @@ struct FrameParams {
   uint32_t* extra_count;       // number of pixels taking the extra-sample branch
   uint32_t* extra_list;        // [n_tiles*1024] pixel slots (tile k * 1024 + q)
   double* extra_samples;       // [extra][max-pre][3]
+  unsigned long long* work_counter;  // [2] persistent-kernel work claim counters (pre pass, extra pass)
   int32_t count_detail;
   int32_t fuse_resolve;        // pre == max == 1 style frames: the trace kernel writes the pixel itself
 };
