@@ -228,20 +228,32 @@ def run_ours(args, rank, local_rank, world_size):
     host_np = host.numpy()
     cam_bytes = C.sizeof(_abi.CameraDesc) + C.sizeof(_abi.RenderOpts)
 
-    def e2e_step():
+    host2 = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+    bufs = [host_np, host2.numpy()]
+    e2e_opts = make_opts(seed=1, precision=precision)
+
+    def e2e_run(n):
+        """n frames through the public frame API with HOST buffers.  N == 1: the pipelined form
+        (rtrb_submit / rtrb_wait, two frames in flight: frame i+1 renders while frame i crosses PCIe);
+        N > 1: every rank renders its tiles into rank 0's framebuffer, rank 0 copies the frame out."""
         if world_size == 1:
-            r.render(cd, make_opts(seed=1, precision=precision), want_rgb=False, want_hit=False, out_rgba=host_np)
+            prev = None
+            for i in range(n):
+                t = r.submit(cd, bufs[i & 1], e2e_opts)
+                if prev is not None:
+                    r.wait(prev)
+                prev = t
+            r.wait(prev)
         else:
-            r.render_device(cd, opts(), want_stats=False)
-            barrier()  # all ranks' tiles have landed in rank 0's framebuffer
-            if rank == 0:
-                check(lib().rtrb_download(r.handle, host_np.ctypes.data, None, None))
-    for _ in range(3):
-        e2e_step()
+            for _ in range(n):
+                r.render_device(cd, opts(), want_stats=False)
+                barrier()  # all ranks' tiles have landed in rank 0's framebuffer
+                if rank == 0:
+                    check(lib().rtrb_download(r.handle, host_np.ctypes.data, None, None))
+    e2e_run(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     barrier()
     e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -258,7 +270,9 @@ def run_ours(args, rank, local_rank, world_size):
                        "rng": "philox4x32-10 counter, seed 1"},
             "frames_per_s": args.steps / (total_ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": cam_bytes,
-                    "d2h_bytes_per_step": W * H * 4, "frames_per_s": args.steps / float(e2e_dt.item())},
+                    "d2h_bytes_per_step": W * H * 4, "frames_per_s": args.steps / float(e2e_dt.item()),
+                    "api": "rtrb_submit/rtrb_wait (2 frames in flight, pinned host buffers)" if world_size == 1 else
+                           "rtrb_render_device per rank + barrier + rtrb_download on rank 0"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s_timed_region": wall,

@@ -193,6 +193,14 @@ int rtrb_download(rtrb_renderer* r, uint8_t* rgba, double* rgb_or_null, int32_t*
 int rtrb_render(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts,
                 uint8_t* rgba, double* rgb_or_null, int32_t* hit_or_null, rtrb_stats* stats_out);
 
+/* Pipelined form of rtrb_render for frame sequences: rtrb_submit launches the frame and queues its
+ * device->host copy into rgba_host (pinned memory recommended) on a separate copy stream, then
+ * returns; rtrb_wait blocks until that frame's bytes and stats are in host memory.  Two frames may be
+ * in flight per renderer, so frame i+1 renders while frame i crosses PCIe.  RGBA8 only. */
+int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts, uint8_t* rgba_host,
+                int* ticket_out);
+int rtrb_wait(rtrb_renderer* r, int ticket, rtrb_stats* stats_out);
+
 /* -- multi-GPU tile gather without a collective ----------------------------------------------- */
 /* Device pointer of the renderer's RGBA8 framebuffer for (width,height) (allocates it if needed). */
 int rtrb_framebuffer_device_ptr(rtrb_renderer* r, int width, int height, void** ptr_out);

@@ -72,10 +72,44 @@ struct DevBuf {
 
 }  // namespace
 
+// Frame control block: every small per-frame device word in ONE buffer (one memset, one D2H copy).
+// u64 words: [0, RTRB_CNT_N) counters | [N] first_bad | [N+1, N+2] work claims | [N+3] = {status, max_stack}
+// | [N+4] = {extra_count, pad}
+#define RTRB_FCB_WORDS (RTRB_CNT_N + 5)
+struct FrameCtl {
+  DevBuf<unsigned long long> d;
+  unsigned long long* h = nullptr;  // pinned host mirror
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr, copied = nullptr;
+  DevBuf<uint8_t> rgba;             // pipeline slots own a framebuffer; the main slot uses rtrb_renderer::rgba
+  // facts of the frame in flight, needed to finish its stats later
+  int W = 0, H = 0, S = 0, E = 0, n_tiles = 0;
+  bool detail = false, in_flight = false;
+  size_t px_count = 0;
+  int init() {
+    cudaError_t e;
+    if ((e = d.ensure(RTRB_FCB_WORDS)) != cudaSuccess) return (int)e;
+    if ((e = cudaMallocHost((void**)&h, RTRB_FCB_WORDS * sizeof(unsigned long long))) != cudaSuccess) return (int)e;
+    cudaEvent_t* evs[5] = {&ev0, &ev1, &evt0, &evt1, &copied};
+    for (auto ev : evs)
+      if ((e = cudaEventCreate(ev)) != cudaSuccess) return (int)e;
+    return 0;
+  }
+  void destroy() {
+    d.release(); rgba.release();
+    if (h) cudaFreeHost(h);
+    h = nullptr;
+    cudaEvent_t* evs[5] = {&ev0, &ev1, &evt0, &evt1, &copied};
+    for (auto ev : evs) { if (*ev) cudaEventDestroy(*ev); *ev = nullptr; }
+  }
+};
+
 struct rtrb_renderer {
   int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  FrameCtl main_ctl;       // synchronous calls
+  FrameCtl pipe_ctl[2];    // rtrb_submit / rtrb_wait double buffering
+  bool pipe_ready = false;
+  unsigned next_ticket = 0;
   // baked scene
   int n_objects = 0, n_lights = 0;
   double max_distance = 0, soft_shadow_exponent = 0;
@@ -97,8 +131,6 @@ struct rtrb_renderer {
   DevBuf<uint32_t> extra_list;
   DevBuf<int32_t> hit;
   DevBuf<uint8_t> rgba;
-  DevBuf<unsigned long long> counters;  // RTRB_CNT_N counters + [RTRB_CNT_N] first_bad
-  DevBuf<uint32_t> status;              // [0] status, [1] max stack, [2] extra_count
   int fb_w = 0, fb_h = 0;
   // last frame
   int last_w = 0, last_h = 0;
@@ -418,8 +450,10 @@ int ensure_framebuffers(rtrb_renderer* r, int w, int h, bool rgb, bool hit) {
   return RTRB_OK;
 }
 
+int finish_stats(rtrb_renderer* r, FrameCtl& fc, rtrb_stats* stats_out);
+
 int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts_in,
-                const FrameTargets* targets, rtrb_stats* stats_out) {
+                const FrameTargets* targets, rtrb_stats* stats_out, FrameCtl* ctl = nullptr) {
   if (!r || !cam) return fail(RTRB_ERR_INVALID, "renderer/camera is NULL");
   rtrb_render_opts opts;
   memset(&opts, 0, sizeof(opts));
@@ -481,8 +515,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   CUDA_TRY(r->samples.ensure(std::max<size_t>(1, n_slots * S * 3)));
   CUDA_TRY(r->extra_list.ensure(std::max<size_t>(1, n_slots)));
   if (E > 0) CUDA_TRY(r->extra_samples.ensure(n_slots * E * 3));
-  CUDA_TRY(r->counters.ensure(RTRB_CNT_N + 3));
-  CUDA_TRY(r->status.ensure(4));
+  FrameCtl& fc = ctl ? *ctl : r->main_ctl;
 
   FrameParams P;
   memset(&P, 0, sizeof(P));
@@ -497,19 +530,19 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.x0 = x0; P.y0 = y0; P.x1 = x1; P.y1 = y1;
   P.n_tiles = n_tiles; P.stx_count = stx_count; P.tiles = r->tiles.p;
   P.samples = r->samples.p; P.rgb = tg.rgb; P.hit = tg.hit; P.rgba = tg.rgba;
-  P.counters = r->counters.p; P.status = r->status.p; P.first_bad = r->counters.p + RTRB_CNT_N;
-  P.work_counter = r->counters.p + RTRB_CNT_N + 1;
-  P.extra_count = r->status.p + 2; P.extra_list = r->extra_list.p; P.extra_samples = r->extra_samples.p;
+  P.counters = fc.d.p; P.first_bad = fc.d.p + RTRB_CNT_N;
+  P.work_counter = fc.d.p + RTRB_CNT_N + 1;
+  P.status = reinterpret_cast<uint32_t*>(fc.d.p + RTRB_CNT_N + 3);
+  P.extra_count = reinterpret_cast<uint32_t*>(fc.d.p + RTRB_CNT_N + 4);
+  P.extra_list = r->extra_list.p; P.extra_samples = r->extra_samples.p;
   P.count_detail = opts.count_detail;
   // a single sample with a positive threshold can never take the adaptive branch (variance == 0)
   P.fuse_resolve = (S == 1 && cam->variant_threshold > 0) ? 1 : 0;
 
   const bool strict = opts.precision == RTRB_PREC_STRICT;
-  CUDA_TRY(cudaEventRecord(r->ev0, stream));
-  CUDA_TRY(cudaMemsetAsync(r->counters.p, 0, RTRB_CNT_N * sizeof(unsigned long long), stream));
-  CUDA_TRY(cudaMemsetAsync(r->counters.p + RTRB_CNT_N, 0xff, sizeof(unsigned long long), stream));
-  CUDA_TRY(cudaMemsetAsync(r->counters.p + RTRB_CNT_N + 1, 0, 2 * sizeof(unsigned long long), stream));
-  CUDA_TRY(cudaMemsetAsync(r->status.p, 0, 4 * sizeof(uint32_t), stream));
+  CUDA_TRY(cudaEventRecord(fc.ev0, stream));
+  CUDA_TRY(cudaMemsetAsync(fc.d.p, 0, RTRB_FCB_WORDS * sizeof(unsigned long long), stream));
+  CUDA_TRY(cudaMemsetAsync(fc.d.p + RTRB_CNT_N, 0xff, sizeof(unsigned long long), stream));
   const bool partial = !(x0 == 0 && y0 == 0 && x1 == W && y1 == H && world == 1);
   if (partial && !tg.no_fill && tg.hit == r->hit.p && tg.hit) {
     size_t n = (size_t)W * H;
@@ -517,9 +550,9 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     g_launches++;
   }
   if (n_tiles > 0) {
-    CUDA_TRY(cudaEventRecord(r->evt0, stream));
+    CUDA_TRY(cudaEventRecord(fc.evt0, stream));
     CUDA_TRY(strict ? rtrb_launch_trace_pre_strict(P, stack_need, stream) : rtrb_launch_trace_pre_fast(P, stack_need, stream));
-    CUDA_TRY(cudaEventRecord(r->evt1, stream));
+    CUDA_TRY(cudaEventRecord(fc.evt1, stream));
     g_launches++;
     if (!P.fuse_resolve) {
       resolve_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, stream>>>(P);
@@ -534,62 +567,68 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
       g_launches++;
     }
   }
-  CUDA_TRY(cudaEventRecord(r->ev1, stream));
+  CUDA_TRY(cudaEventRecord(fc.ev1, stream));
   r->last_w = W; r->last_h = H;
   r->last_has_rgb = tg.rgb == r->rgb.p && tg.rgb != nullptr;
   r->last_has_hit = tg.hit == r->hit.p && tg.hit != nullptr;
   r->last_stream = stream;
 
+  // facts needed to finish the stats once the control block has been copied back
+  fc.W = W; fc.H = H; fc.S = S; fc.E = E; fc.n_tiles = n_tiles; fc.detail = opts.count_detail != 0;
+  fc.px_count = 0;
+  for (int b : r->tiles_host) {
+    int tx = b % stx_count, ty = b / stx_count;
+    int ax0 = std::max(x0, tx * RTRB_SUPER), ax1 = std::min(x1, (tx + 1) * RTRB_SUPER);
+    int ay0 = std::max(y0, ty * RTRB_SUPER), ay1 = std::min(y1, (ty + 1) * RTRB_SUPER);
+    if (ax1 > ax0 && ay1 > ay0) fc.px_count += (size_t)(ax1 - ax0) * (ay1 - ay0);
+  }
   if (stats_out) {
+    CUDA_TRY(cudaMemcpyAsync(fc.h, fc.d.p, RTRB_FCB_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    unsigned long long c[RTRB_CNT_N + 1];
-    uint32_t st[4];
-    CUDA_TRY(cudaMemcpy(c, r->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(st, r->status.p, sizeof(st), cudaMemcpyDeviceToHost));
-    memset(stats_out, 0, sizeof(*stats_out));
-    stats_out->samples = opts.count_detail ? c[RTRB_CNT_SAMPLES] : 0;
-    stats_out->rays = c[RTRB_CNT_RAYS]; stats_out->shadow_queries = c[RTRB_CNT_SHADOW];
-    stats_out->highlight_hits = c[RTRB_CNT_HIGHLIGHT]; stats_out->hits = c[RTRB_CNT_HITS];
-    stats_out->local_shaded = c[RTRB_CNT_LOCAL]; stats_out->lit_lights = c[RTRB_CNT_LIT];
-    stats_out->mc_rays = c[RTRB_CNT_MC]; stats_out->refractions = c[RTRB_CNT_REFR];
-    stats_out->texel_fetches = c[RTRB_CNT_TEXEL];
-    stats_out->sphere_tests = c[RTRB_CNT_SPH_TEST]; stats_out->sphere_accepts = c[RTRB_CNT_SPH_ACC];
-    stats_out->plane_tests = c[RTRB_CNT_PL_TEST]; stats_out->plane_accepts = c[RTRB_CNT_PL_ACC];
-    stats_out->cover_sphere = c[RTRB_CNT_COV_SPH]; stats_out->cover_sphere_full = c[RTRB_CNT_COV_SPH_FULL];
-    stats_out->cover_sphere_penumbra = c[RTRB_CNT_COV_SPH_PEN];
-    stats_out->cover_plane = c[RTRB_CNT_COV_PL]; stats_out->cover_plane_accepts = c[RTRB_CNT_COV_PL_ACC];
-    stats_out->adaptive_pixels = c[RTRB_CNT_ADAPTIVE]; stats_out->exact_tests = c[RTRB_CNT_EXACT];
-    if (!opts.count_detail) {
-      // samples are a pure function of the window when nothing is adaptive; otherwise count_detail reports them
-      size_t px = 0;
-      for (int b : r->tiles_host) {
-        int tx = b % stx_count, ty = b / stx_count;
-        int ax0 = std::max(x0, tx * RTRB_SUPER), ax1 = std::min(x1, (tx + 1) * RTRB_SUPER);
-        int ay0 = std::max(y0, ty * RTRB_SUPER), ay1 = std::min(y1, (ty + 1) * RTRB_SUPER);
-        if (ax1 > ax0 && ay1 > ay0) px += (size_t)(ax1 - ax0) * (ay1 - ay0);
-      }
-      stats_out->samples = (uint64_t)px * S + (uint64_t)(E > 0 ? c[RTRB_CNT_ADAPTIVE] * (uint64_t)E : 0);
-    }
-    stats_out->status = st[0];
-    stats_out->max_stack = st[1];
-    if (st[0] && c[RTRB_CNT_N] != ~0ull) {
-      stats_out->first_bad_x = (int32_t)(c[RTRB_CNT_N] / (unsigned long long)H);
-      stats_out->first_bad_y = (int32_t)(c[RTRB_CNT_N] % (unsigned long long)H);
-    } else {
-      stats_out->first_bad_x = stats_out->first_bad_y = -1;
-    }
-    float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
-    stats_out->device_ms = ms;
-    if (n_tiles > 0) {
-      CUDA_TRY(cudaEventElapsedTime(&ms, r->evt0, r->evt1));
-      stats_out->trace_ms = ms;
-    }
-    if (st[0]) {
-      fail(RTRB_ERR_RAISED, "the reference would have raised: status 0x%x at pixel (%d, %d)", st[0],
-           stats_out->first_bad_x, stats_out->first_bad_y);
-      return RTRB_ERR_RAISED;
-    }
+    return finish_stats(r, fc, stats_out);
+  }
+  return RTRB_OK;
+}
+
+// Turns a copied-back control block into rtrb_stats (+ RTRB_ERR_RAISED when a status bit is set).
+int finish_stats(rtrb_renderer* r, FrameCtl& fc, rtrb_stats* stats_out) {
+  (void)r;
+  const unsigned long long* c = fc.h;
+  const uint32_t* st = reinterpret_cast<const uint32_t*>(fc.h + RTRB_CNT_N + 3);
+  memset(stats_out, 0, sizeof(*stats_out));
+  stats_out->rays = c[RTRB_CNT_RAYS]; stats_out->shadow_queries = c[RTRB_CNT_SHADOW];
+  stats_out->highlight_hits = c[RTRB_CNT_HIGHLIGHT]; stats_out->hits = c[RTRB_CNT_HITS];
+  stats_out->local_shaded = c[RTRB_CNT_LOCAL]; stats_out->lit_lights = c[RTRB_CNT_LIT];
+  stats_out->mc_rays = c[RTRB_CNT_MC]; stats_out->refractions = c[RTRB_CNT_REFR];
+  stats_out->texel_fetches = c[RTRB_CNT_TEXEL];
+  stats_out->sphere_tests = c[RTRB_CNT_SPH_TEST]; stats_out->sphere_accepts = c[RTRB_CNT_SPH_ACC];
+  stats_out->plane_tests = c[RTRB_CNT_PL_TEST]; stats_out->plane_accepts = c[RTRB_CNT_PL_ACC];
+  stats_out->cover_sphere = c[RTRB_CNT_COV_SPH]; stats_out->cover_sphere_full = c[RTRB_CNT_COV_SPH_FULL];
+  stats_out->cover_sphere_penumbra = c[RTRB_CNT_COV_SPH_PEN];
+  stats_out->cover_plane = c[RTRB_CNT_COV_PL]; stats_out->cover_plane_accepts = c[RTRB_CNT_COV_PL_ACC];
+  stats_out->adaptive_pixels = c[RTRB_CNT_ADAPTIVE]; stats_out->exact_tests = c[RTRB_CNT_EXACT];
+  // samples: counted on the device with count_detail; otherwise a pure function of the window
+  stats_out->samples = fc.detail ? c[RTRB_CNT_SAMPLES]
+                                 : (uint64_t)fc.px_count * fc.S + (uint64_t)(fc.E > 0 ? c[RTRB_CNT_ADAPTIVE] * (uint64_t)fc.E : 0);
+  stats_out->status = st[0];
+  stats_out->max_stack = st[1];
+  if (st[0] && c[RTRB_CNT_N] != ~0ull) {
+    stats_out->first_bad_x = (int32_t)(c[RTRB_CNT_N] / (unsigned long long)fc.H);
+    stats_out->first_bad_y = (int32_t)(c[RTRB_CNT_N] % (unsigned long long)fc.H);
+  } else {
+    stats_out->first_bad_x = stats_out->first_bad_y = -1;
+  }
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, fc.ev0, fc.ev1));
+  stats_out->device_ms = ms;
+  if (fc.n_tiles > 0) {
+    CUDA_TRY(cudaEventElapsedTime(&ms, fc.evt0, fc.evt1));
+    stats_out->trace_ms = ms;
+  }
+  if (st[0]) {
+    fail(RTRB_ERR_RAISED, "the reference would have raised: status 0x%x at pixel (%d, %d)", st[0],
+         stats_out->first_bad_x, stats_out->first_bad_y);
+    return RTRB_ERR_RAISED;
   }
   return RTRB_OK;
 }
@@ -628,9 +667,9 @@ int rtrb_renderer_create(const rtrb_scene_desc* scene, int device, rtrb_renderer
   r->device = device;
   cudaError_t ce;
   if ((ce = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (ce = cudaEventCreate(&r->ev0)) != cudaSuccess || (ce = cudaEventCreate(&r->ev1)) != cudaSuccess ||
-      (ce = cudaEventCreate(&r->evt0)) != cudaSuccess || (ce = cudaEventCreate(&r->evt1)) != cudaSuccess) {
-    delete r;
+      (ce = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (ce = (cudaError_t)r->main_ctl.init()) != cudaSuccess) {
+    rtrb_renderer_destroy(r);
     return fail(RTRB_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(ce));
   }
   rc = bake_scene(r, scene);
@@ -646,13 +685,10 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   r->geom.release(); r->mat.release(); r->lights.release();
   r->cull_sph.release(); r->cull_pl.release(); r->sph_index.release(); r->pl_index.release(); r->lights_f.release(); r->tiles.release(); r->samples.release();
   r->extra_samples.release(); r->rgb.release(); r->extra_list.release(); r->hit.release(); r->rgba.release();
-  r->counters.release(); r->status.release();
+  r->main_ctl.destroy(); r->pipe_ctl[0].destroy(); r->pipe_ctl[1].destroy();
   for (uint8_t* t : r->textures) cudaFree(t);
-  if (r->ev0) cudaEventDestroy(r->ev0);
-  if (r->ev1) cudaEventDestroy(r->ev1);
-  if (r->evt0) cudaEventDestroy(r->evt0);
-  if (r->evt1) cudaEventDestroy(r->evt1);
   if (r->stream) cudaStreamDestroy(r->stream);
+  if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
   delete r;
   return RTRB_OK;
 }
@@ -695,6 +731,59 @@ int rtrb_render(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   if (rc2) return rc2;
   if (rc == RTRB_ERR_RAISED) g_last_error = keep;
   return rc;
+}
+
+int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts, uint8_t* rgba_host,
+                int* ticket_out) {
+  if (!r || !cam || !rgba_host || !ticket_out) return fail(RTRB_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(r->device));
+  if (!r->pipe_ready) {
+    for (int i = 0; i < 2; ++i) {
+      cudaError_t e = (cudaError_t)r->pipe_ctl[i].init();
+      if (e != cudaSuccess) return fail(RTRB_ERR_CUDA, "pipeline slot init failed: %s", cudaGetErrorString(e));
+    }
+    r->pipe_ready = true;
+  }
+  const unsigned ticket = r->next_ticket;
+  FrameCtl& fc = r->pipe_ctl[ticket & 1u];
+  if (fc.in_flight) return fail(RTRB_ERR_INVALID, "two frames are already in flight: call rtrb_wait first");
+  const size_t bytes = (size_t)cam->width * cam->height * 4;
+  if (cam->width > 0 && cam->height > 0 && fc.rgba.n < bytes) {
+    CUDA_TRY(fc.rgba.ensure(bytes));
+    CUDA_TRY(cudaMemsetAsync(fc.rgba.p, 0, bytes, r->stream));
+  }
+  rtrb_render_opts o;
+  memset(&o, 0, sizeof(o));
+  if (opts) o = *opts;
+  else { o.seed = 1; o.precision = RTRB_PREC_DEFAULT; }
+  o.stream = nullptr;  // the pipeline owns its streams
+  FrameTargets tg;
+  tg.rgba = o.rgba_device_out ? (uint8_t*)o.rgba_device_out : fc.rgba.p;
+  tg.want_rgb = false; tg.want_hit = false;
+  int rc = render_impl(r, cam, &o, &tg, nullptr, &fc);
+  if (rc) return rc;
+  // the copy stream picks the frame up as soon as its kernels are done; the render stream is free
+  // to start the next frame into the other slot meanwhile
+  CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, fc.ev1, 0));
+  CUDA_TRY(cudaMemcpyAsync(rgba_host, tg.rgba, bytes, cudaMemcpyDeviceToHost, r->copy_stream));
+  CUDA_TRY(cudaMemcpyAsync(fc.h, fc.d.p, RTRB_FCB_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->copy_stream));
+  CUDA_TRY(cudaEventRecord(fc.copied, r->copy_stream));
+  // (the slot is reused only after rtrb_wait has host-synchronised on `copied`, so no stream wait is needed)
+  fc.in_flight = true;
+  r->next_ticket = ticket + 1;
+  *ticket_out = (int)ticket;
+  return RTRB_OK;
+}
+
+int rtrb_wait(rtrb_renderer* r, int ticket, rtrb_stats* stats_out) {
+  if (!r || !r->pipe_ready) return fail(RTRB_ERR_INVALID, "nothing submitted");
+  FrameCtl& fc = r->pipe_ctl[(unsigned)ticket & 1u];
+  if (!fc.in_flight) return fail(RTRB_ERR_INVALID, "ticket %d is not in flight", ticket);
+  CUDA_TRY(cudaSetDevice(r->device));
+  CUDA_TRY(cudaEventSynchronize(fc.copied));
+  fc.in_flight = false;
+  rtrb_stats local;
+  return finish_stats(r, fc, stats_out ? stats_out : &local);
 }
 
 int rtrb_framebuffer_device_ptr(rtrb_renderer* r, int width, int height, void** ptr_out) {

@@ -5,7 +5,10 @@
 
 namespace {
 
-constexpr int kBlock = 128;
+#ifndef RTRB_FAST_BLOCK
+#define RTRB_FAST_BLOCK 128
+#endif
+constexpr int kBlock = RTRB_FAST_BLOCK;
 #ifndef RTRB_FAST_MIN_BLOCKS
 #define RTRB_FAST_MIN_BLOCKS 4
 #endif

@@ -89,6 +89,20 @@ class Renderer:
         check(code, allow_raised=True)
         return Frame(rgba, rgb, hit, st.as_dict(), code)
 
+    def submit(self, cam, out_rgba, opts=None):
+        """Pipelined frame: returns a ticket at once; the RGBA8 frame lands in `out_rgba` (a numpy view
+        of pinned host memory for full speed) by the time `wait(ticket)` returns.  Two in flight."""
+        opts = opts or make_opts()
+        t = C.c_int()
+        check(lib().rtrb_submit(self._h, C.byref(cam), C.byref(opts), out_rgba.ctypes.data, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        st = _abi.Stats()
+        code = lib().rtrb_wait(self._h, ticket, C.byref(st))
+        check(code, allow_raised=True)
+        return st.as_dict(), code
+
     def framebuffer_ptr(self, width, height):
         p = C.c_void_p()
         check(lib().rtrb_framebuffer_device_ptr(self._h, width, height, C.byref(p)))
