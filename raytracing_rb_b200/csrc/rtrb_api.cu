@@ -118,6 +118,7 @@ struct rtrb_renderer {
   DevBuf<DevLight> lights;
   // FP32 filter view (FAST64)
   DevBuf<float4> cull_sph, cull_pl;
+  DevBuf<BvhNode> bvh;
   DevBuf<int32_t> sph_index, pl_index;
   DevBuf<DevLightF> lights_f;
   int n_sph = 0, n_pl = 0;
@@ -343,12 +344,14 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
   // ---- FP32 filter view: conversions round to nearest; the filter's margins cover that error ----
   std::vector<float4> csph, cpl;
   std::vector<int32_t> isph, ipl;
+  std::vector<BvhBuildSphere> bsph;
   float m_scene = 0.0f;
   for (int i = 0; i < s->n_objects; ++i) {
     const rtrb_object_desc& o = s->objects[i];
     if (o.type == RTRB_OBJ_SPHERE) {
-      csph.push_back(make_float4((float)o.point[0], (float)o.point[1], (float)o.point[2], (float)o.radius));
-      isph.push_back(i);
+      BvhBuildSphere bs;
+      bs.c[0] = o.point[0]; bs.c[1] = o.point[1]; bs.c[2] = o.point[2]; bs.r = o.radius; bs.world_index = i;
+      bsph.push_back(bs);
       double cm = fmax(fabs(o.point[0]), fmax(fabs(o.point[1]), fabs(o.point[2]))) + fabs(o.radius);
       m_scene = fmaxf(m_scene, nextafterf((float)cm, INFINITY));
     } else {
@@ -359,6 +362,14 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
       ipl.push_back(i);
     }
   }
+  // the BVH build reorders the spheres so that every leaf is a contiguous run of cull_sph[]
+  std::vector<BvhNode> nodes = rtrb_bvh::build_tree(bsph);
+  for (const BvhBuildSphere& bs : bsph) {
+    csph.push_back(make_float4((float)bs.c[0], (float)bs.c[1], (float)bs.c[2], (float)bs.r));
+    isph.push_back(bs.world_index);
+  }
+  CUDA_TRY(r->bvh.ensure(std::max<size_t>(1, nodes.size())));
+  if (!nodes.empty()) CUDA_TRY(cudaMemcpy(r->bvh.p, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
   r->n_sph = (int)isph.size(); r->n_pl = (int)ipl.size();
   r->m_scene = m_scene;
   r->max_distance_f = nextafterf((float)s->max_distance, INFINITY);
@@ -524,7 +535,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.n_objects = r->n_objects; P.n_lights = r->n_lights;
   P.geom = r->geom.p; P.mat = r->mat.p; P.lights = r->lights.p;
   P.cull_sph = r->cull_sph.p; P.sph_index = r->sph_index.p; P.cull_pl = r->cull_pl.p; P.pl_index = r->pl_index.p;
-  P.lights_f = r->lights_f.p; P.n_sph = r->n_sph; P.n_pl = r->n_pl;
+  P.lights_f = r->lights_f.p; P.n_sph = r->n_sph; P.n_pl = r->n_pl; P.bvh = r->bvh.p;
   P.m_scene = r->m_scene; P.max_distance_f = r->max_distance_f;
   P.key0 = (uint32_t)opts.seed; P.key1 = (uint32_t)(opts.seed >> 32);
   P.x0 = x0; P.y0 = y0; P.x1 = x1; P.y1 = y1;
@@ -683,6 +694,7 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
   r->geom.release(); r->mat.release(); r->lights.release();
+  r->bvh.release();
   r->cull_sph.release(); r->cull_pl.release(); r->sph_index.release(); r->pl_index.release(); r->lights_f.release(); r->tiles.release(); r->samples.release();
   r->extra_samples.release(); r->rgb.release(); r->extra_list.release(); r->hit.release(); r->rgba.release();
   r->main_ctl.destroy(); r->pipe_ctl[0].destroy(); r->pipe_ctl[1].destroy();

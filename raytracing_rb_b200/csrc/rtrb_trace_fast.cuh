@@ -161,27 +161,106 @@ static __device__ __noinline__ int closest_hit_scan(const FrameParams& P, d3 o, 
   return best_i;
 }
 
-// World#intersect (world.rb:37-59) = FP32 filter over every object + exact test of the survivors.
+// ---- sphere BVH traversal (filter only; see rtrb_bvh.h for why it cannot change a result) ----------
+struct BvhRay {
+  float ox, oy, oz, ix, iy, iz, E;
+};
+__device__ __forceinline__ BvhRay make_bvh_ray(const CullRay& r) {
+  BvhRay b;
+  b.ox = r.ox; b.oy = r.oy; b.oz = r.oz;
+  b.ix = rcp_approx(r.dx); b.iy = rcp_approx(r.dy); b.iz = rcp_approx(r.dz);
+  b.E = r.E;
+  return b;
+}
+// Slab test of the segment t in [tmin, tmax] against the box fattened by E on every side.
+__device__ __forceinline__ bool box_hit(float lx, float ly, float lz, float hx, float hy, float hz, const BvhRay& b,
+                                        float tmin, float tmax, float& tn_out) {
+  const float t0x = (lx - b.E - b.ox) * b.ix, t1x = (hx + b.E - b.ox) * b.ix;
+  const float t0y = (ly - b.E - b.oy) * b.iy, t1y = (hy + b.E - b.oy) * b.iy;
+  const float t0z = (lz - b.E - b.oz) * b.iz, t1z = (hz + b.E - b.oz) * b.iz;
+  const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+  const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+  tn_out = tn;
+  return tn <= tf;
+}
+
+#define RTRB_BVH_STACK 32
+
+// Visits every sphere whose (fattened) bounds the segment [tmin, tmax] of the ray touches, nearest
+// subtree first.  `leaf(k)` is called with the sphere's slot in cull_sph[] and may shrink `tmax`.
+// Returns false when the traversal stack would overflow (caller falls back to the exact scan).
+template <typename Leaf>
+__device__ __forceinline__ bool bvh_traverse(const FrameParams& P, const BvhRay& b, float tmin, float& tmax, Leaf leaf) {
+  if (P.n_sph == 0) return true;
+  int stk[RTRB_BVH_STACK];
+  int sp = 0;
+  int cur = 0;  // root
+  while (true) {
+    const float4* np = reinterpret_cast<const float4*>(P.bvh + cur);
+    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+    const int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
+    float tn0, tn1;
+    const bool h0 = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, b, tmin, tmax, tn0);
+    const bool h1 = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, b, tmin, tmax, tn1);
+    int first = n3.x, second = n3.y;
+    bool hf = h0, hs = h1;
+    if (h0 && h1 && tn1 < tn0) { first = n3.y; second = n3.x; }
+    if (!h0) { first = n3.y; hf = h1; hs = false; }
+    int next = -1;  // internal node to descend into
+    if (hf) {
+      if (first < 0) {
+        const uint32_t v = (uint32_t)(~first);
+        const uint32_t f0 = v & 0xFFFFFu, cnt = v >> 20;
+        for (uint32_t j = 0; j < cnt; ++j) leaf(f0 + j);
+      } else {
+        next = first;
+      }
+    }
+    if (hs) {
+      if (second < 0) {
+        const uint32_t v = (uint32_t)(~second);
+        const uint32_t f0 = v & 0xFFFFFu, cnt = v >> 20;
+        for (uint32_t j = 0; j < cnt; ++j) leaf(f0 + j);
+      } else if (next < 0) {
+        next = second;
+      } else {
+        if (sp >= RTRB_BVH_STACK) return false;
+        stk[sp++] = second;
+      }
+    }
+    if (next >= 0) { cur = next; continue; }
+    if (sp == 0) break;
+    cur = stk[--sp];
+  }
+  return true;
+}
+
+// World#intersect (world.rb:37-59) = FP32 filter (planes + sphere BVH) + exact test of the survivors.
 __device__ __forceinline__ int closest_hit_fast(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx) {
-  Pack8 S;
-  S.clear();
-  if (P.n_sph > 65535) return closest_hit_scan(P, o, d, bh, ctx);
-#pragma unroll 4
-  for (int k = 0; k < P.n_sph; ++k) {
-    const float4 s = __ldg(&P.cull_sph[k]);
-    if (!sphere_line_misses(s, r)) S.push((uint32_t)k);
-  }
-  if (S.overflow() || P.n_pl > 8) return closest_hit_scan(P, o, d, bh, ctx);
-  // pass 1: the smallest certain upper bound; nothing at or beyond max_distance can win (world.rb:39)
+  if (P.n_sph > 0xFFFFF || P.n_pl > 8) return closest_hit_scan(P, o, d, bh, ctx);
+  // pass 1a: planes bound the search first (nothing at or beyond max_distance can win, world.rb:39)
   float best_hi = P.max_distance_f;
-  for (int c = 0; c < S.n; ++c) {
-    float lo, hi;
-    if (classify_sphere(__ldg(&P.cull_sph[S.get(c)]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
-  }
   for (int k = 0; k < P.n_pl; ++k) {
     float lo, hi;
     if (classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
+  }
+  // pass 1b: spheres through the BVH; certain hits keep shrinking the search interval
+  Pack8 S;
+  S.clear();
+  {
+    const BvhRay b = make_bvh_ray(r);
+    float tmax = best_hi + r.E;
+    const bool ok = bvh_traverse(P, b, -r.E, tmax, [&](uint32_t k) {
+      const float4 s = __ldg(&P.cull_sph[k]);
+      float lo, hi;
+      const int kind = classify_sphere(s, r, lo, hi);
+      if (kind != 0 && lo <= best_hi) {
+        S.push(k);
+        if (kind == 2 && hi < best_hi) { best_hi = hi; tmax = hi + r.E; }
+      }
+    });
+    if (!ok || S.overflow()) return closest_hit_scan(P, o, d, bh, ctx);
   }
   // pass 2: exact FP64 evaluation of whatever can still win; (distance, index) lexicographic order
   // reproduces the strict `<` scan in world_objects order.
@@ -239,14 +318,20 @@ __device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target,
     const float lx = (float)c.lt.x, ly = (float)c.lt.y, lz = (float)c.lt.z;
     far = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) * 1.00001f + 2.0f * r.E;
   }
-  if (P.n_sph > 65535 || P.n_pl > 65535) return lit_area(P, target, L, ctx);
+  if (P.n_sph > 0xFFFFF || P.n_pl > 0xFFFF) return lit_area(P, target, L, ctx);
   Pack8 S, Q;
   S.clear();
   Q.clear();
-#pragma unroll 4
-  for (int k = 0; k < P.n_sph; ++k) {
-    const float4 s = __ldg(&P.cull_sph[k]);
-    if (!sphere_line_misses(s, r)) S.push((uint32_t)k);
+  {
+    const BvhRay b = make_bvh_ray(r);
+    float tmax = far + r.E;
+    const bool ok = bvh_traverse(P, b, -r.E, tmax, [&](uint32_t k) {
+      const float4 s = __ldg(&P.cull_sph[k]);
+      float lo, hi;
+      const int kind = classify_sphere(s, r, lo, hi);
+      if (kind != 0 && !(lo > far)) S.push(k);
+    });
+    if (!ok) return lit_area(P, target, L, ctx);
   }
   for (int k = 0; k < P.n_pl; ++k) {
     float lo, hi;
@@ -256,28 +341,22 @@ __device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target,
   if (S.overflow() || Q.overflow()) return lit_area(P, target, L, ctx);
   double total = 1;
   bool have_n = false;
-  int cs = 0, cq = 0;
-  // merge the two survivor lists (each ascending in world_objects index) so covers subtract in order
-  while (cs < S.n || cq < Q.n) {
-    const int is = cs < S.n ? P.sph_index[S.get(cs)] : 0x7fffffff;
-    const int iq = cq < Q.n ? P.pl_index[Q.get(cq)] : 0x7fffffff;
-    if (is < iq) {
-      const uint32_t k = S.get(cs++);
-      float lo, hi;
-      const int kind = classify_sphere(__ldg(&P.cull_sph[k]), r, lo, hi);
-      if (kind == 0 || lo > far) continue;
-      if (!have_n) {
-        c.lt_r = norm(c.lt);
-        c.ltn = mk(c.lt.x / c.lt_r, c.lt.y / c.lt_r, c.lt.z / c.lt_r);
-        have_n = true;
-      }
-      RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-      total -= cover_object_exact(P.geom[is], c, L.radius, ctx);
-    } else {
-      cq++;
-      RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-      total -= cover_object_exact(P.geom[iq], c, L.radius, ctx);
+  // visit the survivors in ascending world_objects index (selection over <= 16 entries)
+  int last = -1;
+  while (true) {
+    int best_idx = 0x7fffffff;
+    for (int a = 0; a < S.n; ++a) { const int i = P.sph_index[S.get(a)]; if (i > last && i < best_idx) best_idx = i; }
+    for (int a = 0; a < Q.n; ++a) { const int i = P.pl_index[Q.get(a)]; if (i > last && i < best_idx) best_idx = i; }
+    if (best_idx == 0x7fffffff) break;
+    last = best_idx;
+    const DevGeom g = P.geom[best_idx];
+    if (g.type == RTRB_OBJ_SPHERE && !have_n) {
+      c.lt_r = norm(c.lt);
+      c.ltn = mk(c.lt.x / c.lt_r, c.lt.y / c.lt_r, c.lt.z / c.lt_r);
+      have_n = true;
     }
+    RTRB_COUNT(ctx, RTRB_CNT_EXACT);
+    total -= cover_object_exact(g, c, L.radius, ctx);
   }
   return fmax(total, 0.0);
 }

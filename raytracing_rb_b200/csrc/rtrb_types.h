@@ -10,6 +10,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "rtrb_bvh.h"
+
 #define RTRB_MAX_LIGHTS 64
 #define RTRB_SUPER 32                 // super-tile edge in pixels (tile partition unit across GPUs)
 #define RTRB_SUPER_PIXELS (RTRB_SUPER * RTRB_SUPER)
@@ -80,6 +82,7 @@ struct FrameParams {
   const float4* cull_pl;       // [2*n_pl] (nx, ny, nz, |n|_1), (px, py, pz, |P|_inf)
   const int32_t* pl_index;     // [n_pl]
   const DevLightF* lights_f;   // [n_lights]
+  const struct BvhNode* bvh;   // sphere BVH over cull_sph[] (rtrb_bvh.h); node 0 = root
   int32_t n_sph, n_pl;
   float m_scene;               // max over spheres of |C|_inf + R  (error-bound scale)
   float max_distance_f;        // max_distance rounded up to float
