@@ -126,7 +126,9 @@ struct rtrb_renderer {
   std::vector<uint8_t*> textures;
   // per-frame scratch
   DevBuf<int32_t> tiles;
-  std::vector<int32_t> tiles_host;
+  std::vector<int32_t> tiles_host;     // global ids ty * stx_count + tx
+  DevBuf<double> lens_tab;             // [W + H] per-column / per-row retina offsets
+  double lens_key[4] = {0, 0, 0, 0};   // (W, H, retina_width, retina_height) the table was built for
   int tiles_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
   DevBuf<double> samples, extra_samples, rgb;
   DevBuf<uint32_t> extra_list;
@@ -311,6 +313,11 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
     }
     m.refractive_rate = o.refractive_rate;
     m.has_refraction = o.has_refraction;
+    if (o.type == RTRB_OBJ_PLANE) {
+      H3 f = h3(o.front);
+      m.plane_nn_valid = hnorm(f) != 0 ? 1 : 0;
+      if (m.plane_nn_valid) put(m.plane_nn, hnormalize(f));
+    }
     m.u_unit = o.u_unit; m.v_unit = o.v_unit;
     m.hscale = o.texture_horizontal_scale; m.vscale = o.texture_vertical_scale;
     m.uoff = o.texture_u_offset; m.voff = o.texture_v_offset;
@@ -511,11 +518,29 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   if (memcmp(key, r->tiles_key, sizeof(key)) != 0) {
     enumerate_tiles(W, x0, y0, x1, y1, rank, world, r->tiles_host);
     CUDA_TRY(r->tiles.ensure(std::max<size_t>(1, r->tiles_host.size())));
-    if (!r->tiles_host.empty())
-      CUDA_TRY(cudaMemcpyAsync(r->tiles.p, r->tiles_host.data(), r->tiles_host.size() * sizeof(int32_t),
-                               cudaMemcpyHostToDevice, stream));
+    if (!r->tiles_host.empty()) {
+      std::vector<int32_t> packed(r->tiles_host.size());
+      for (size_t i = 0; i < packed.size(); ++i)
+        packed[i] = (r->tiles_host[i] % stx_count) | ((r->tiles_host[i] / stx_count) << 16);
+      CUDA_TRY(cudaMemcpyAsync(r->tiles.p, packed.data(), packed.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(stream));
     memcpy(r->tiles_key, key, sizeof(key));
+  }
+  // ---- lens tables (cached): the per-column / per-row scalars of camera.rb:133-134, evaluated on the
+  // host in the reference's order so the device does two loads instead of two FP64 divisions per sample
+  {
+    double lk[4] = {(double)W, (double)H, cam->retina_width, cam->retina_height};
+    if (memcmp(lk, r->lens_key, sizeof(lk)) != 0 || !r->lens_tab.p) {
+      std::vector<double> tab((size_t)W + H);
+      for (int x = 0; x < W; ++x) tab[x] = 2.0 * ((double)x / W - 0.5) * cam->retina_width;
+      for (int y = 0; y < H; ++y) tab[(size_t)W + y] = 2 * ((double)y / H - 0.5) * cam->retina_height;
+      CUDA_TRY(r->lens_tab.ensure(tab.size()));
+      CUDA_TRY(cudaMemcpyAsync(r->lens_tab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      memcpy(r->lens_key, lk, sizeof(lk));
+    }
   }
   const int n_tiles = (int)r->tiles_host.size();
   const size_t n_slots = (size_t)n_tiles * RTRB_SUPER_PIXELS;
@@ -540,6 +565,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.key0 = (uint32_t)opts.seed; P.key1 = (uint32_t)(opts.seed >> 32);
   P.x0 = x0; P.y0 = y0; P.x1 = x1; P.y1 = y1;
   P.n_tiles = n_tiles; P.stx_count = stx_count; P.tiles = r->tiles.p;
+  P.lens_sx = r->lens_tab.p; P.lens_sy = r->lens_tab.p + W;
   P.samples = r->samples.p; P.rgb = tg.rgb; P.hit = tg.hit; P.rgba = tg.rgba;
   P.counters = fc.d.p; P.first_bad = fc.d.p + RTRB_CNT_N;
   P.work_counter = fc.d.p + RTRB_CNT_N + 1;
@@ -693,7 +719,7 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   if (!r) return RTRB_OK;
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
-  r->geom.release(); r->mat.release(); r->lights.release();
+  r->geom.release(); r->mat.release(); r->lights.release(); r->lens_tab.release();
   r->bvh.release();
   r->cull_sph.release(); r->cull_pl.release(); r->sph_index.release(); r->pl_index.release(); r->lights_f.release(); r->tiles.release(); r->samples.release();
   r->extra_samples.release(); r->rgb.release(); r->extra_list.release(); r->hit.release(); r->rgba.release();

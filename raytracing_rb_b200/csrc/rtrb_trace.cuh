@@ -440,10 +440,15 @@ __device__ __forceinline__ d3 trace_sample(const FrameParams& P, d3 ro, d3 rd, u
 // Camera#lens_func (camera.rb:129-151) for pixel (x, y) and aperture angle theta.
 __device__ __forceinline__ void lens_ray(const FrameParams& P, int x, int y, double theta, d3& ro, d3& rd) {
   d3 pos = ld3(P.pos), left = ld3(P.left), upn = ld3(P.up_n), front = ld3(P.front);
-  double sx = 2.0 * ((double)x / P.width - 0.5) * P.retina_width;
-  double sy = 2 * ((double)y / P.height - 0.5) * P.retina_height;
+  // host-built tables of 2.0 * (x.to_f / width - 0.5) * retina_width and the y analogue (camera.rb:133-134)
+  const double sx = P.lens_sx[x];
+  const double sy = P.lens_sy[y];
   d3 retina_position = (ld3(P.retina_center) + left * sx) + upn * sy;
-  d3 rand_vector = (ld3(P.left_n) * cos(theta) + upn * sin(theta)) * P.aperture_radius;  // (finite)*0.0 when pinhole
+  // aperture_radius == 0.0 (pinhole): the reference still evaluates (left*cos + up*sin) * 0.0 = (+-0, +-0, +-0);
+  // adding a zero of either sign to `pos` gives `pos` (up to the sign of an exact zero, which no later
+  // expression can observe), so the two FP64 transcendentals are skipped.
+  d3 rand_vector = mk(0.0, 0.0, 0.0);
+  if (P.aperture_radius != 0.0) rand_vector = (ld3(P.left_n) * cos(theta) + upn * sin(theta)) * P.aperture_radius;
   d3 aperture = pos + rand_vector;
   d3 rf = pos - retina_position;  // ray retina -> lens centre
   double t = dot(ld3(P.focal_point) - retina_position, front) / dot(front, rf);  // intersect_plane :123-127
@@ -470,11 +475,11 @@ __device__ __forceinline__ void write_pixel(const FrameParams& P, int x, int y, 
 // Decodes work item -> (tile slot k, in-tile q, x, y); returns false when the pixel is outside the window.
 __device__ __forceinline__ bool decode_pixel(const FrameParams& P, uint32_t slot, int& x, int& y) {
   uint32_t k = slot / RTRB_SUPER_PIXELS, q = slot % RTRB_SUPER_PIXELS;
-  int tile = P.tiles[k];
+  const uint32_t tile = (uint32_t)P.tiles[k];  // tx | ty << 16
   int qx, qy;
   rtrb_morton_decode(q, &qx, &qy);
-  x = (tile % P.stx_count) * RTRB_SUPER + qx;
-  y = (tile / P.stx_count) * RTRB_SUPER + qy;
+  x = (int)(tile & 0xffffu) * RTRB_SUPER + qx;
+  y = (int)(tile >> 16) * RTRB_SUPER + qy;
   return x >= P.x0 && x < P.x1 && y >= P.y0 && y < P.y1;
 }
 
@@ -542,9 +547,12 @@ __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
     active = decode_pixel(P, slot, x, y);
     if (active) {
       const uint32_t pixel = (uint32_t)y * (uint32_t)P.width + (uint32_t)x;
-      uint32_t c0 = pixel, c1 = j, c2 = 0u, c3 = 0u;
-      philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
-      double theta = res53(c0, c1);  // Random.rand, camera.rb:135
+      double theta = 0.0;
+      if (P.aperture_radius != 0.0) {
+        uint32_t c0 = pixel, c1 = j, c2 = 0u, c3 = 0u;
+        philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
+        theta = res53(c0, c1);  // Random.rand, camera.rb:135
+      }
       d3 ro, rd;
       lens_ray(P, x, y, theta, ro, rd);
       int ph;
@@ -580,9 +588,12 @@ __device__ __forceinline__ void trace_extra_body(const FrameParams& P) {
     if (!decode_pixel(P, slot, x, y)) continue;
     any = true;
     const uint32_t pixel = (uint32_t)y * (uint32_t)P.width + (uint32_t)x;
-    uint32_t c0 = pixel, c1 = j, c2 = 0u, c3 = 0u;
-    philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
-    double theta = res53(c0, c1);
+    double theta = 0.0;
+    if (P.aperture_radius != 0.0) {
+      uint32_t c0 = pixel, c1 = j, c2 = 0u, c3 = 0u;
+      philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
+      theta = res53(c0, c1);
+    }
     d3 ro, rd;
     lens_ray(P, x, y, theta, ro, rd);
     int ph;

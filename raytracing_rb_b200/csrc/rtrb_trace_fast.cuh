@@ -344,19 +344,29 @@ __device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target,
   // visit the survivors in ascending world_objects index (selection over <= 16 entries)
   int last = -1;
   while (true) {
-    int best_idx = 0x7fffffff;
-    for (int a = 0; a < S.n; ++a) { const int i = P.sph_index[S.get(a)]; if (i > last && i < best_idx) best_idx = i; }
-    for (int a = 0; a < Q.n; ++a) { const int i = P.pl_index[Q.get(a)]; if (i > last && i < best_idx) best_idx = i; }
+    int best_idx = 0x7fffffff, best_k = -1;
+    for (int a = 0; a < S.n; ++a) {
+      const int k = (int)S.get(a), i = P.sph_index[k];
+      if (i > last && i < best_idx) { best_idx = i; best_k = k; }
+    }
+    for (int a = 0; a < Q.n; ++a) {
+      const int i = P.pl_index[Q.get(a)];
+      if (i > last && i < best_idx) { best_idx = i; best_k = -1; }
+    }
     if (best_idx == 0x7fffffff) break;
     last = best_idx;
-    const DevGeom g = P.geom[best_idx];
-    if (g.type == RTRB_OBJ_SPHERE && !have_n) {
-      c.lt_r = norm(c.lt);
-      c.ltn = mk(c.lt.x / c.lt_r, c.lt.y / c.lt_r, c.lt.z / c.lt_r);
-      have_n = true;
+    if (best_k >= 0) {  // sphere: the full classification may still prove factor == 0
+      float lo, hi;
+      const int kind = classify_sphere(__ldg(&P.cull_sph[best_k]), r, lo, hi);
+      if (kind == 0 || lo > far) continue;
+      if (!have_n) {
+        c.lt_r = norm(c.lt);
+        c.ltn = mk(c.lt.x / c.lt_r, c.lt.y / c.lt_r, c.lt.z / c.lt_r);
+        have_n = true;
+      }
     }
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-    total -= cover_object_exact(g, c, L.radius, ctx);
+    total -= cover_object_exact(P.geom[best_idx], c, L.radius, ctx);
   }
   return fmax(total, 0.0);
 }
@@ -454,7 +464,14 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
       rate = M.refractive_rate;
       can_refract = M.has_refraction != 0;
     }
-    const d3 nn = normalize(n, ctx);
+    d3 nn;
+    if (g.type != RTRB_OBJ_SPHERE && M.plane_nn_valid) {
+      // n is +-front: its normalisation is a per-plane constant baked on the host (-(x / r) == (-x) / r)
+      const d3 pn = ld3(M.plane_nn);
+      nn = (n.x == g.nx && n.y == g.ny && n.z == g.nz) ? pn : -pn;
+    } else {
+      nn = normalize(n, ctx);
+    }
 
     // ---- children (ray_tracer.rb:87-121), computed only if they can survive the cut at :52.
     // A child with trace_depth - 1 <= 0, or whose attenuation norm is certainly < 1e-4, is popped and

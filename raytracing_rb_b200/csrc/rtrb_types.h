@@ -32,10 +32,11 @@ struct DevMat {
   double e0[3], e1[3], e2[3];
   double u_unit, v_unit;
   double hscale, vscale, uoff, voff;
+  double plane_nn[3];   // plane only: normalize(front); normalize(-front) is its exact negation
   const uint8_t* tex;   // device pointer to rows of RGB8, or nullptr
   int32_t tex_w, tex_h;
   int32_t has_refraction;
-  int32_t pad;
+  int32_t plane_nn_valid;  // 0 when front is the zero vector: the runtime normalize must run (and flag)
 };
 
 struct DevLight {
@@ -92,7 +93,9 @@ struct FrameParams {
   int32_t x0, y0, x1, y1;      // window
   int32_t n_tiles;             // super-tiles assigned to this renderer for this frame
   int32_t stx_count;           // super-tiles per row of the full image
-  const int32_t* tiles;        // [n_tiles] global super-tile ids (sty * stx_count + stx)
+  const int32_t* tiles;        // [n_tiles] super-tile coordinates packed as tx | ty << 16
+  const double* lens_sx;       // [width]  2.0 * (x.to_f / width - 0.5) * retina_width    camera.rb:133
+  const double* lens_sy;       // [height] 2 * (y.to_f / height - 0.5) * retina_height    camera.rb:134
   // outputs / scratch
   double* samples;             // [n_tiles * 1024 * S][3] per-sample colours of the current pass
   double* rgb;                 // [H][W][3] or nullptr
