@@ -22,6 +22,10 @@
 #include "rtrb_trace.cuh"
 #include "rtrb_types.h"
 
+// Scenes with at most this many spheres use the linear-scan filter kernels and keep cull_sph[] in
+// world order; larger scenes get the BVH kernels (measured crossover, see rtrb_trace_fast.cuh).
+#define RTRB_BVH_MIN_SPHERES 32
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -370,7 +374,8 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
     }
   }
   // the BVH build reorders the spheres so that every leaf is a contiguous run of cull_sph[]
-  std::vector<BvhNode> nodes = rtrb_bvh::build_tree(bsph);
+  std::vector<BvhNode> nodes;
+  if ((int)bsph.size() > RTRB_BVH_MIN_SPHERES) nodes = rtrb_bvh::build_tree(bsph);
   for (const BvhBuildSphere& bs : bsph) {
     csph.push_back(make_float4((float)bs.c[0], (float)bs.c[1], (float)bs.c[2], (float)bs.r));
     isph.push_back(bs.world_index);
@@ -562,6 +567,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.cull_sph = r->cull_sph.p; P.sph_index = r->sph_index.p; P.cull_pl = r->cull_pl.p; P.pl_index = r->pl_index.p;
   P.lights_f = r->lights_f.p; P.n_sph = r->n_sph; P.n_pl = r->n_pl; P.bvh = r->bvh.p;
   P.m_scene = r->m_scene; P.max_distance_f = r->max_distance_f;
+  P.use_bvh = r->n_sph > RTRB_BVH_MIN_SPHERES ? 1 : 0;
   P.key0 = (uint32_t)opts.seed; P.key1 = (uint32_t)(opts.seed >> 32);
   P.x0 = x0; P.y0 = y0; P.x1 = x1; P.y1 = y1;
   P.n_tiles = n_tiles; P.stx_count = stx_count; P.tiles = r->tiles.p;

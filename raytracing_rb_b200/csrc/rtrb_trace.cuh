@@ -521,19 +521,21 @@ __device__ __forceinline__ void init_ctx(ThreadCtx& ctx, bool detail) {
 }
 
 // FAST64 entry point, defined in rtrb_trace_fast.cuh (only instantiated by that translation unit).
-template <int MAXS>
+template <int MAXS, bool BVH>
 __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
                                                 ThreadCtx& ctx, int* primary_hit);
 
-template <int MAXS, bool FAST>
+// MODE: 0 = STRICT, 1 = FAST64 with the linear filter, 2 = FAST64 with the sphere BVH
+template <int MAXS, int MODE>
 __device__ __forceinline__ d3 trace_dispatch(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
                                              ThreadCtx& ctx, int* primary_hit) {
-  if constexpr (FAST) return trace_sample_fast<MAXS>(P, ro, rd, pixel, sample, ctx, primary_hit);
+  if constexpr (MODE == 2) return trace_sample_fast<MAXS, true>(P, ro, rd, pixel, sample, ctx, primary_hit);
+  else if constexpr (MODE == 1) return trace_sample_fast<MAXS, false>(P, ro, rd, pixel, sample, ctx, primary_hit);
   else return trace_sample<MAXS>(P, ro, rd, pixel, sample, ctx, primary_hit);
 }
 
 // One thread per (pixel, sample j < pre_sample_times): the first loop of render_at (camera.rb:73-78).
-template <int MAXS, bool DETAIL, bool FAST = false>
+template <int MAXS, bool DETAIL, int MODE = 0>
 __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
   const uint32_t S = (uint32_t)P.pre;
   const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -556,7 +558,7 @@ __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
       d3 ro, rd;
       lens_ray(P, x, y, theta, ro, rd);
       int ph;
-      d3 col = trace_dispatch<MAXS, FAST>(P, ro, rd, pixel, j, ctx, &ph);
+      d3 col = trace_dispatch<MAXS, MODE>(P, ro, rd, pixel, j, ctx, &ph);
       RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
       if (P.fuse_resolve) {
         // one sample, positive threshold: mean = s / 1.0 = s and variance = 0 < threshold (camera.rb:80-87)
@@ -573,7 +575,7 @@ __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
 
 // Extra samples j in [pre, max) of the pixels that failed the variance test (camera.rb:88-93);
 // persistent grid-stride loop because the pixel count is only known on the device.
-template <int MAXS, bool DETAIL, bool FAST = false>
+template <int MAXS, bool DETAIL, int MODE = 0>
 __device__ __forceinline__ void trace_extra_body(const FrameParams& P) {
   const uint32_t E = (uint32_t)(P.max_samples - P.pre);
   const unsigned long long total = (unsigned long long)(*P.extra_count) * E;
@@ -597,7 +599,7 @@ __device__ __forceinline__ void trace_extra_body(const FrameParams& P) {
     d3 ro, rd;
     lens_ray(P, x, y, theta, ro, rd);
     int ph;
-    d3 col = trace_dispatch<MAXS, FAST>(P, ro, rd, pixel, j, ctx, &ph);
+    d3 col = trace_dispatch<MAXS, MODE>(P, ro, rd, pixel, j, ctx, &ph);
     RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
     double* out = P.extra_samples + w * 3ull;
     out[0] = col.x; out[1] = col.y; out[2] = col.z;

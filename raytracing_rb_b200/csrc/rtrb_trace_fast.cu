@@ -13,13 +13,13 @@ constexpr int kBlock = RTRB_FAST_BLOCK;
 #define RTRB_FAST_MIN_BLOCKS 4
 #endif
 
-template <int MAXS, bool DETAIL>
+template <int MAXS, bool DETAIL, bool BVH>
 __global__ void __launch_bounds__(kBlock, RTRB_FAST_MIN_BLOCKS) trace_pre_fast_kernel(const __grid_constant__ FrameParams P) {
-  rtrb::trace_pre_body<MAXS, DETAIL, true>(P);
+  rtrb::trace_pre_body<MAXS, DETAIL, BVH ? 2 : 1>(P);
 }
-template <int MAXS, bool DETAIL>
+template <int MAXS, bool DETAIL, bool BVH>
 __global__ void __launch_bounds__(kBlock, RTRB_FAST_MIN_BLOCKS) trace_extra_fast_kernel(const __grid_constant__ FrameParams P) {
-  rtrb::trace_extra_body<MAXS, DETAIL, true>(P);
+  rtrb::trace_extra_body<MAXS, DETAIL, BVH ? 2 : 1>(P);
 }
 
 // A persistent-thread variant (lanes refetch a new sample when their stack empties) was measured in
@@ -33,7 +33,8 @@ cudaError_t launch_pre(const FrameParams& P, cudaStream_t s) {
   if (total == 0) return cudaSuccess;
   unsigned long long blocks = (total + kBlock - 1) / kBlock;
   if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-  trace_pre_fast_kernel<MAXS, DETAIL><<<(unsigned)blocks, kBlock, 0, s>>>(P);
+  if (P.use_bvh) trace_pre_fast_kernel<MAXS, DETAIL, true><<<(unsigned)blocks, kBlock, 0, s>>>(P);
+  else trace_pre_fast_kernel<MAXS, DETAIL, false><<<(unsigned)blocks, kBlock, 0, s>>>(P);
   return cudaGetLastError();
 }
 template <int MAXS, bool DETAIL>
@@ -41,7 +42,8 @@ cudaError_t launch_extra(const FrameParams& P, cudaStream_t s) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  trace_extra_fast_kernel<MAXS, DETAIL><<<sms * 8, kBlock, 0, s>>>(P);
+  if (P.use_bvh) trace_extra_fast_kernel<MAXS, DETAIL, true><<<sms * 8, kBlock, 0, s>>>(P);
+  else trace_extra_fast_kernel<MAXS, DETAIL, false><<<sms * 8, kBlock, 0, s>>>(P);
   return cudaGetLastError();
 }
 

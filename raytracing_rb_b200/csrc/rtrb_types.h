@@ -85,6 +85,7 @@ struct FrameParams {
   const DevLightF* lights_f;   // [n_lights]
   const struct BvhNode* bvh;   // sphere BVH over cull_sph[] (rtrb_bvh.h); node 0 = root
   int32_t n_sph, n_pl;
+  int32_t use_bvh, pad_bvh;    // > RTRB_BVH_MIN_SPHERES spheres: BVH kernels; else the linear-scan kernels
   float m_scene;               // max over spheres of |C|_inf + R  (error-bound scale)
   float max_distance_f;        // max_distance rounded up to float
   // rng
