@@ -47,36 +47,60 @@ def algorithmic_flops(s):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons DURING the timed region through NVML (nvidia-ml-py), every
+    ~2 ms; falls back to polling nvidia-smi when NVML is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        if self.nv is not None:
+            nv = self.nv
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for name, bit in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+        else:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_power_cap,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.hw_thermal_slowdown")
+            out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                           "--format=csv,noheader,nounits"], timeout=5).decode()
+            r = [x.strip() for x in out.strip().split(",")]
+            self.sm.append(float(r[0]))
+            self.max_mhz = float(r[1])
+            for (name, _), v in zip(self.REASONS, r[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                               "--format=csv,noheader,nounits"], timeout=5).decode()
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                self._sample()
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.002)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def workload(config_id, small):

@@ -500,6 +500,7 @@ __device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, 
     atomicMax(&P.status[1], ms);
   }
   if (ctx.detail) {
+#pragma unroll
     for (int i = 0; i < RTRB_CNT_N; ++i) {
       if (i == RTRB_CNT_RAYS || i == RTRB_CNT_SHADOW) continue;
       uint32_t v = ctx.c[i];
@@ -516,8 +517,10 @@ __device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, 
 
 __device__ __forceinline__ void init_ctx(ThreadCtx& ctx, bool detail) {
   ctx.status = 0; ctx.rays = 0; ctx.shadow = 0; ctx.max_stack = 0; ctx.detail = detail;
+  if (detail) {  // the lean kernels never touch c[]: no zeroing, no local-memory array
 #pragma unroll
-  for (int i = 0; i < RTRB_CNT_N; ++i) ctx.c[i] = 0;
+    for (int i = 0; i < RTRB_CNT_N; ++i) ctx.c[i] = 0;
+  }
 }
 
 // FAST64 entry point, defined in rtrb_trace_fast.cuh (only instantiated by that translation unit).

@@ -52,6 +52,7 @@ cudaError_t launch_extra(const FrameParams& P, cudaStream_t s) {
 #define RTRB_DISPATCH(fn, P, need, s)                                         \
   do {                                                                        \
     const bool det = (P).count_detail != 0;                                   \
+    if ((P).trace_depth <= 1) return det ? fn<1, true>(P, s) : fn<1, false>(P, s); \
     if ((need) <= 10) return det ? fn<10, true>(P, s) : fn<10, false>(P, s);  \
     if ((need) <= 32) return det ? fn<32, true>(P, s) : fn<32, false>(P, s);  \
     return det ? fn<128, true>(P, s) : fn<128, false>(P, s);                  \

@@ -620,7 +620,23 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
     const bool refr_alive = depth_ok && !(sumsq(a_refr) < 0.99e-8);
     const double dn_dot = dot(d, n);
     const bool near_normal = !(dn_dot * dn_dot < (1.0 - 1e-9) * (sumsq(d) * sumsq(n)));  // possible raise site
-    if (refl_alive || refr_alive || near_normal) {
+    if constexpr (MAXS == 1) {
+      // trace_depth <= 1: every child is born with depth 0 and dropped at ray_tracer.rb:52; only the
+      // raise sites of their direction math can be observed, and only near normal incidence
+      if (near_normal) {
+        const double d_r = norm(d);
+        const double cos_theta = vcos(d, -n, ctx);
+        const d3 refl_dir = normalize(nn * (2 * cos_theta * d_r) + d, ctx);
+        if (can_refract) {
+          const double sin_i = rb_sqrt(1 - cos_theta * cos_theta, ctx);
+          const double sin_r = sin_i / rate;
+          if (!(sin_r >= 1)) {
+            if (sin_r < -1 || sin_r > 1) ctx.status |= RTRB_ST_MATH_DOMAIN;
+            (void)normalize(refl_dir + d, ctx);
+          }
+        }
+      }
+    } else if (refl_alive || refr_alive || near_normal) {
       if (sp + 2 > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; return; }
       const double d_r = norm(d);
       const double cos_theta = vcos(d, -n, ctx);  // == vcos(d, n): both square the dot product
@@ -671,7 +687,8 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
       }
     }
     if (n_lit == 0) {
-      if (P.mc > 0) {
+      if (MAXS == 1 && P.mc > 0 && ctx.detail) ctx.c[RTRB_CNT_MC] += P.mc;  // spawned, born dead
+      if (MAXS > 1 && P.mc > 0) {
         if (sp + P.mc > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; return; }
         const d3 att_pt = ld3(M.diffuse) / (double)P.mc;
         const d3 a2 = att * att_pt;
@@ -730,20 +747,24 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
 template <int MAXS, bool BVH>
 __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
                                                 ThreadCtx& ctx, int* primary_hit) {
-  StackItem stack[MAXS];
-  stack[0].ox = ro.x; stack[0].oy = ro.y; stack[0].oz = ro.z;
-  stack[0].dx = rd.x; stack[0].dy = rd.y; stack[0].dz = rd.z;
-  stack[0].ax = 1.0; stack[0].ay = 1.0; stack[0].az = 1.0;
-  stack[0].depth = P.trace_depth; stack[0].path = 1u;
-  int sp = 1;
+  StackItem stack[MAXS > 1 ? MAXS : 1];
+  // the root item starts in registers (no round trip through the local-memory stack)
+  StackItem it;
+  it.ox = ro.x; it.oy = ro.y; it.oz = ro.z;
+  it.dx = rd.x; it.dy = rd.y; it.dz = rd.z;
+  it.ax = 1.0; it.ay = 1.0; it.az = 1.0;
+  it.depth = P.trace_depth; it.path = 1u;
+  int sp = 0;
   d3 sum = mk(0.0, 0.0, 0.0);
   bool first = true;
   *primary_hit = -1;
-  while (sp > 0) {
-    if ((uint32_t)sp > ctx.max_stack) ctx.max_stack = (uint32_t)sp;
-    const StackItem it = stack[--sp];
+  ctx.max_stack = max(ctx.max_stack, 1u);
+  while (true) {
     process_item_fast<MAXS, BVH>(P, it, stack, sp, sum, ctx, pixel, sample, first, primary_hit);
     first = false;
+    if (MAXS == 1 || sp == 0) break;
+    if ((uint32_t)sp > ctx.max_stack) ctx.max_stack = (uint32_t)sp;
+    it = stack[--sp];
   }
   return sum;
 }

@@ -199,3 +199,19 @@ def test_pipelined_submit_wait_matches_blocking_render():
         assert np.array_equal(got[k], want[k].rgba), k
         assert stats[k]["rays"] == want[k].stats["rays"] and stats[k]["shadow_queries"] == want[k].stats["shadow_queries"]
     assert not np.array_equal(got[0], got[-1])
+
+
+@pytest.mark.parametrize("precision", [PREC_STRICT, PREC_FAST64])
+def test_depth1_with_mc_rays(oracle_mod, precision):
+    """trace_depth 1 with Monte-Carlo rays configured: every child is born dead, but the counters
+    (mc_rays spawned) and the image must still match the oracle (exercises the depth-1 kernel)."""
+    from raytracing_rb_b200 import Camera, World, scenes
+    wdoc, cdoc = scenes.build(4, width=160, height=90)
+    cdoc["trace_depth"] = 1
+    cdoc["pre_sample_times"] = cdoc["max_sample_times"] = 2
+    world = World(wdoc)
+    cam = Camera(world, cdoc)
+    ref = oracle_mod.OracleScene(world.to_scene_desc()).render(cam.camera_desc(), make_opts(seed=9))
+    got = cam.render_frame(seed=9, precision=precision, count_detail=True)
+    check(ref, got, precision == PREC_STRICT)
+    assert got.stats["mc_rays"] == ref.stats["mc_rays"] > 0
