@@ -459,10 +459,11 @@ __device__ __forceinline__ void lens_ray(const FrameParams& P, int x, int y, dou
 
 // array_to_color (camera.rb:153-156) + the byte truncation of PNG::Color.new
 __device__ __forceinline__ uint8_t quantise_u8(double c) {
-  double x = c * 256.0;
-  double m = (255.0 < x) ? 255.0 : x;  // [x, 255].min
-  if (!(m > 0)) return 0;
-  return (uint8_t)(int)m;
+  // [c*256, 255].min truncated to a byte; negatives and NaN give 0.  c*256 is an exact scaling, and the
+  // saturating round-toward-zero conversion followed by an integer clamp is the same function.
+  int v = __double2int_rz(c * 256.0);  // NaN -> 0, +-inf / out of range saturate
+  v = v < 0 ? 0 : (v > 255 ? 255 : v);
+  return (uint8_t)v;
 }
 // render_at's result for pixel (x, y): row = y, column = x (camera.rb:98,105)
 __device__ __forceinline__ void write_pixel(const FrameParams& P, int x, int y, double r, double g, double b) {
@@ -486,13 +487,8 @@ __device__ __forceinline__ bool decode_pixel(const FrameParams& P, uint32_t slot
 __device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, int x, int y, bool active) {
   // warp-aggregate the two lean counters, then one atomic per warp
   const unsigned full = 0xffffffffu;
-  uint32_t rays = ctx.rays, shadow = ctx.shadow, ms = ctx.max_stack;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    rays += __shfl_xor_sync(full, rays, o);
-    shadow += __shfl_xor_sync(full, shadow, o);
-    ms = max(ms, __shfl_xor_sync(full, ms, o));
-  }
+  const uint32_t rays = __reduce_add_sync(full, ctx.rays), shadow = __reduce_add_sync(full, ctx.shadow),
+                 ms = __reduce_max_sync(full, ctx.max_stack);
   const int lane = threadIdx.x & 31;
   if (lane == 0) {
     if (rays) atomicAdd(&P.counters[RTRB_CNT_RAYS], (unsigned long long)rays);
@@ -503,9 +499,7 @@ __device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, 
 #pragma unroll
     for (int i = 0; i < RTRB_CNT_N; ++i) {
       if (i == RTRB_CNT_RAYS || i == RTRB_CNT_SHADOW) continue;
-      uint32_t v = ctx.c[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+      const uint32_t v = __reduce_add_sync(full, ctx.c[i]);
       if (lane == 0 && v) atomicAdd(&P.counters[i], (unsigned long long)v);
     }
   }
@@ -548,7 +542,9 @@ __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
   int x = 0, y = 0;
   bool active = false;
   if (w < total) {
-    const uint32_t slot = (uint32_t)(w / S), j = (uint32_t)(w % S);
+    uint32_t slot, j;
+    if (S == 1u) { slot = (uint32_t)w; j = 0u; }
+    else { slot = (uint32_t)(w / S); j = (uint32_t)(w - (unsigned long long)slot * S); }
     active = decode_pixel(P, slot, x, y);
     if (active) {
       const uint32_t pixel = (uint32_t)y * (uint32_t)P.width + (uint32_t)x;
