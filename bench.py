@@ -154,11 +154,21 @@ def run_reference(args, rank, world_size):
     print(json.dumps(line))
 
 
+def batch_cameras(world, cdoc, n):
+    """The step's batch: n frames of the workload with the camera dollying sideways (a short fly-by)."""
+    from raytracing_rb_b200 import Camera
+    cams = []
+    for f in range(n):
+        c = Camera(world, cdoc).camera_desc()
+        c.position[1] = c.position[1] + 0.02 * f
+        cams.append(c)
+    return cams
+
+
 def run_ours(args, rank, local_rank, world_size):
     import torch
-    from raytracing_rb_b200 import (Camera, Renderer, _abi, ipc_open, make_opts, measure_fma_peak, PREC_FAST64,
-                                    PREC_STRICT)
-    from raytracing_rb_b200._lib import lib, check
+    from raytracing_rb_b200 import (Renderer, _abi, ipc_open, make_opts, measure_fma_peak, PREC_FAST64, PREC_STRICT)
+    from raytracing_rb_b200._lib import lib
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -170,25 +180,29 @@ def run_ours(args, rank, local_rank, world_size):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     precision = PREC_STRICT if args.precision == "strict" else PREC_FAST64
     world, cdoc, name = workload(args.config, args.small)
-    cd = Camera(world, cdoc).camera_desc()
-    W, H = cd.width, cd.height
+    B = max(1, args.frames_per_step)
+    cams = batch_cameras(world, cdoc, B)
+    W, H = cams[0].width, cams[0].height
+    frame_bytes = W * H * 4
     r = Renderer(world.to_scene_desc(), local_rank)
 
-    # ---- where the pixels go: rank 0's framebuffer (peer mapping for the other ranks) ----
-    peer_ptr = None
+    # ---- where the pixels go: B frame slots in rank 0's framebuffer (a peer mapping for the others) ----
+    if rank == 0:
+        base_ptr = r.framebuffer_ptr(W, H * B)
     if world_size > 1:
         hbuf = torch.zeros(64, dtype=torch.uint8, device="cuda")
         if rank == 0:
-            hbuf.copy_(torch.frombuffer(bytearray(r.framebuffer_ipc_export(W, H)), dtype=torch.uint8))
+            hbuf.copy_(torch.frombuffer(bytearray(r.framebuffer_ipc_export(W, H * B)), dtype=torch.uint8))
         dist.broadcast(hbuf, 0)
         if rank != 0:
-            peer_ptr = ipc_open(local_rank, bytes(hbuf.cpu().numpy().tobytes()))
+            base_ptr = ipc_open(local_rank, bytes(hbuf.cpu().numpy().tobytes()))
     stream = torch.cuda.Stream()  # a real (non-NULL) stream: NULL means "the renderer's own stream" in the C ABI
     torch.cuda.set_stream(stream)
 
-    def opts(detail=False):
-        return make_opts(seed=1, precision=precision, tile_rank=rank, tile_world=world_size, count_detail=detail,
-                         stream=stream.cuda_stream, rgba_device_out=peer_ptr)
+    def opts(f, detail=False, prec=None):
+        return make_opts(seed=1, precision=precision if prec is None else prec, tile_rank=rank, tile_world=world_size,
+                         count_detail=detail, stream=stream.cuda_stream, rgba_device_out=base_ptr + f * frame_bytes,
+                         skip_outputs=_abi.SKIP_RGB | _abi.SKIP_HIT)
 
     def barrier():
         torch.cuda.synchronize()
@@ -196,20 +210,25 @@ def run_ours(args, rank, local_rank, world_size):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- untimed: per-frame work of this rank (counters) and the FMA issue peaks ----
-    # the algorithmic (brute-force) operation counts come from the STRICT kernel's detailed counters:
-    # FAST64 produces the same frame with fewer executed tests, which must not shrink the numerator
-    so = opts(True)
-    so.precision = PREC_STRICT
-    st_detail, _ = r.render_device(cd, so)
-    flops_frame = algorithmic_flops(st_detail)
-    rays_frame = st_detail["rays"] + st_detail["shadow_queries"]
+    # ---- untimed: this rank's work per batch (counters) and the FMA issue peaks ----
+    # The algorithmic (brute-force) operation counts come from the STRICT kernel's detailed counters:
+    # FAST64 produces the same frames with fewer executed tests, which must not shrink the numerator.
+    flops_batch, rays_batch = 0, 0
+    for f in range(B):
+        st, _ = r.render_device(cams[f], opts(f, True, PREC_STRICT))
+        flops_batch += algorithmic_flops(st)
+        rays_batch += st["rays"] + st["shadow_queries"]
     peak64 = measure_fma_peak(local_rank, True) if rank == 0 else 0.0
     peak32 = measure_fma_peak(local_rank, False) if rank == 0 else 0.0
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    step_opts = [opts(f) for f in range(B)]
+
+    def step():
+        for f in range(B):
+            r.render_device(cams[f], step_opts[f], want_stats=False)
     for _ in range(max(args.warmup, 3)):
-        r.render_device(cd, opts(), want_stats=False)
+        step()
     barrier()
 
     # ---- timed: EXACTLY K steps, CUDA events on the launch stream, L2 flushed between steps ----
@@ -218,63 +237,63 @@ def run_ours(args, rank, local_rank, world_size):
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    o = opts()
     barrier()
     wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()
         ev[k][0].record(stream)
-        r.render_device(cd, o, want_stats=False)
+        step()
         ev[k][1].record(stream)
     barrier()
     wall = time.perf_counter() - wall0
     launches = lib().rtrb_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
-    rays_t = torch.tensor([float(rays_frame), float(flops_frame)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(rays_batch), float(flops_batch), float(launches)], dtype=torch.float64, device="cuda")
     if dist is not None:
-        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # a frame is done when its slowest rank is
-        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # a step is done when its slowest rank is
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     total_ms = float(step_ms.sum().item())
-    rays_total, flops_total = float(rays_t[0].item()), float(rays_t[1].item())
+    rays_total, flops_total, launches_total = (float(x) for x in tot.tolist())
     value = rays_total * args.steps / (total_ms * 1e-3) / 1e6
 
-    # ---- dominant kernel alone (trace over the pre samples): library-side CUDA events ----
+    # ---- dominant kernel alone (trace over the pre samples): library-side CUDA events, cold L2 ----
     tr = []
-    for _ in range(min(args.steps, 20)):
-        flush.zero_()
-        st, _ = r.render_device(cd, opts())
-        tr.append(st["trace_ms"])
+    for k in range(min(args.steps, 10)):
+        for f in range(B):
+            flush.zero_()
+            st, _ = r.render_device(cams[f], opts(f))
+            tr.append(st["trace_ms"])
     trace_ms = float(np.mean(tr))
 
     # ---- e2e: the public frame call with HOST buffers (pinned), copies inside the timed region ----
-    host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
-    host_np = host.numpy()
     cam_bytes = C.sizeof(_abi.CameraDesc) + C.sizeof(_abi.RenderOpts)
-
-    host2 = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
-    bufs = [host_np, host2.numpy()]
     e2e_opts = make_opts(seed=1, precision=precision)
+    if world_size == 1:
+        bufs = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+    elif rank == 0:
+        host_batch = torch.empty((H * B, W, 4), dtype=torch.uint8).pin_memory().numpy()
 
-    def e2e_run(n):
-        """n frames through the public frame API with HOST buffers.  N == 1: the pipelined form
-        (rtrb_submit / rtrb_wait, two frames in flight: frame i+1 renders while frame i crosses PCIe);
-        N > 1: every rank renders its tiles into rank 0's framebuffer, rank 0 copies the frame out."""
+    def e2e_run(n_steps):
+        """N == 1: the pipelined frame API (rtrb_submit / rtrb_wait, two frames in flight: frame i+1
+        renders while frame i crosses PCIe).  N > 1: every rank renders its tiles of the B frames into
+        rank 0's frame slots, then rank 0 copies the batch to the host."""
         if world_size == 1:
-            prev = None
-            for i in range(n):
-                t = r.submit(cd, bufs[i & 1], e2e_opts)
-                if prev is not None:
-                    r.wait(prev)
-                prev = t
+            prev, i = None, 0
+            for _ in range(n_steps):
+                for f in range(B):
+                    t = r.submit(cams[f], bufs[i & 1], e2e_opts)
+                    if prev is not None:
+                        r.wait(prev)
+                    prev, i = t, i + 1
             r.wait(prev)
         else:
-            for _ in range(n):
-                r.render_device(cd, opts(), want_stats=False)
-                barrier()  # all ranks' tiles have landed in rank 0's framebuffer
+            for _ in range(n_steps):
+                step()
+                barrier()  # all ranks' tiles have landed in rank 0's frame slots
                 if rank == 0:
-                    check(lib().rtrb_download(r.handle, host_np.ctypes.data, None, None))
-    e2e_run(3)
+                    r.framebuffer_download(W, H * B, host_batch)
+    e2e_run(1)
     barrier()
     t0 = time.perf_counter()
     e2e_run(args.steps)
@@ -282,38 +301,52 @@ def run_ours(args, rank, local_rank, world_size):
     e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    e2e_value = rays_total * args.steps / float(e2e_dt.item()) / 1e6
+    e2e_s = float(e2e_dt.item())
+    e2e_value = rays_total * args.steps / e2e_s / 1e6
 
     if rank == 0:
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "precision_mode": args.precision, "rays_per_frame": rays_total,
-                       "l2": "flushed between timed steps (256 MiB write)", "tiles": "32x32 px round-robin over ranks",
+            "config": {"workload": name + "; one step = a batch of %d frames (camera dolly)" % B,
+                       "frames_per_step": B, "precision_mode": args.precision, "rays_per_step": rays_total,
+                       "l2": "flushed between timed steps (256 MiB write)",
+                       "tiles": "32x32 px super-tiles dealt round-robin over ranks, peer stores into rank 0's framebuffer",
                        "rng": "philox4x32-10 counter, seed 1"},
-            "frames_per_s": args.steps / (total_ms * 1e-3),
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": cam_bytes,
-                    "d2h_bytes_per_step": W * H * 4, "frames_per_s": args.steps / float(e2e_dt.item()),
+            "frames_per_s": args.steps * B / (total_ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": cam_bytes * B,
+                    "d2h_bytes_per_step": frame_bytes * B, "frames_per_s": args.steps * B / e2e_s,
                     "api": "rtrb_submit/rtrb_wait (2 frames in flight, pinned host buffers)" if world_size == 1 else
-                           "rtrb_render_device per rank + barrier + rtrb_download on rank 0"},
-            "gpu_launches": int(launches),
+                           "rtrb_render_device per rank into rank 0's frame slots + barrier + rtrb_framebuffer_download"},
+            "gpu_launches": int(launches_total),
             "clocks": clocks,
             "wall_s_timed_region": wall,
         }
         if world_size == 1:
+            flops_frame = flops_batch / B
             achieved = flops_frame / (trace_ms * 1e-3) / 1e12
             line["roofline"] = {
-                "bound": "fp64", "kernel": "trace_pre_*_kernel", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
+                "bound": "fp64", "kernel": "trace_pre_fast_kernel", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
                 "frac": achieved / peak64 if peak64 else None, "traffic": None,
                 "peak_source": "measured in this job: dependent-free DFMA microbenchmark (rtrb_measure_fma_peak)",
                 "peak_fp32": peak32, "algorithmic_flops_per_launch": flops_frame, "kernel_ms": trace_ms,
+                "hbm": {"algorithmic_bytes_per_launch": frame_bytes, "peak_gbs": measured_hbm_gbs(),
+                        "achieved_gbs": frame_bytes / (trace_ms * 1e-3) / 1e9},
                 "note": "FP-issue bound path (SURVEY.md 8d): HBM traffic is the 4 B/pixel framebuffer write only",
             }
-            line["cpu_baseline"] = cpu_baseline(args, world, cd, name)
+            line["cpu_baseline"] = cpu_baseline(args, world, cams[0], name)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def measured_hbm_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"]
+    except Exception:
+        return 6650.0  # fallback stated in B200_PROFILING.md
 
 
 def cpu_baseline(args, world, cd, name):
@@ -344,7 +377,8 @@ def cpu_baseline(args, world, cd, name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--frames-per-step", type=int, default=16, help="frames rendered per timed step")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2)

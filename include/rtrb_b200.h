@@ -58,6 +58,9 @@ enum {
   RTRB_RNG_MT = 1    /* MT19937 genrand_res53 in the reference's consumption order; oracle only */
 };
 
+/* ---- rtrb_render_opts.skip_outputs ----------------------------------------------------------- */
+enum { RTRB_SKIP_RGB = 1, RTRB_SKIP_HIT = 2 };
+
 /* ---- arithmetic modes of the device path ---------------------------------------------------- */
 enum {
   RTRB_PREC_STRICT = 0,   /* FP64, no FMA contraction, every div/sqrt as the reference writes it */
@@ -135,7 +138,8 @@ typedef struct rtrb_render_opts {
    * rtrb_tile_partition). tile_world <= 1 = everything. */
   int32_t tile_rank, tile_world;
   int32_t count_detail; /* 1 = fill every rtrb_stats counter (slower); 0 = rays/shadow/samples only */
-  int32_t reserved0;
+  int32_t skip_outputs; /* rtrb_render_device only: RTRB_SKIP_RGB | RTRB_SKIP_HIT drop the optional float RGB
+                           (24 B/pixel) / hit-id (4 B/pixel) frames; 0 keeps both for rtrb_download */
   void* stream;         /* cudaStream_t to launch on; NULL = the renderer's own stream */
   void* rgba_device_out;/* device pointer (possibly a peer mapping) the RGBA8 frame is written to;
                            NULL = the renderer's own framebuffer */
@@ -204,6 +208,10 @@ int rtrb_wait(rtrb_renderer* r, int ticket, rtrb_stats* stats_out);
 /* -- multi-GPU tile gather without a collective ----------------------------------------------- */
 /* Device pointer of the renderer's RGBA8 framebuffer for (width,height) (allocates it if needed). */
 int rtrb_framebuffer_device_ptr(rtrb_renderer* r, int width, int height, void** ptr_out);
+/* Copies width*height*4 bytes of that framebuffer to host memory (blocking).  With a framebuffer
+ * allocated for (width, height * n) this fetches n frames that were rendered into consecutive slots
+ * through rgba_device_out. */
+int rtrb_framebuffer_download(rtrb_renderer* r, int width, int height, uint8_t* rgba_host);
 /* CUDA IPC handle (64 bytes) of that framebuffer, to hand to the other per-GPU processes. */
 int rtrb_framebuffer_ipc_export(rtrb_renderer* r, int width, int height, uint8_t handle_out[64]);
 /* Maps a peer process's framebuffer into this process; pass the result as rgba_device_out. */

@@ -16,6 +16,7 @@ OBJ_PLANE, OBJ_SPHERE = 0, 1
 RNG_CTR, RNG_MT = 0, 1
 PREC_STRICT, PREC_FAST64 = 0, 1
 PREC_DEFAULT = PREC_FAST64
+SKIP_RGB, SKIP_HIT = 1, 2
 
 D3 = C.c_double * 3
 
@@ -70,7 +71,7 @@ class RenderOpts(C.Structure):
         ("rng_mode", C.c_int32), ("precision", C.c_int32), ("seed", C.c_uint64),
         ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32),
         ("tile_rank", C.c_int32), ("tile_world", C.c_int32),
-        ("count_detail", C.c_int32), ("reserved0", C.c_int32),
+        ("count_detail", C.c_int32), ("skip_outputs", C.c_int32),
         ("stream", C.c_void_p), ("rgba_device_out", C.c_void_p),
     ]
 

@@ -507,6 +507,10 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
 
   FrameTargets tg;
   if (targets) tg = *targets;
+  else {
+    tg.want_rgb = !(opts.skip_outputs & RTRB_SKIP_RGB);
+    tg.want_hit = !(opts.skip_outputs & RTRB_SKIP_HIT);
+  }
   {
     int rc = ensure_framebuffers(r, W, H, tg.want_rgb && !tg.rgb, tg.want_hit && !tg.hit);
     if (rc) return rc;
@@ -583,9 +587,10 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.fuse_resolve = (S == 1 && cam->variant_threshold > 0) ? 1 : 0;
 
   const bool strict = opts.precision == RTRB_PREC_STRICT;
-  CUDA_TRY(cudaEventRecord(fc.ev0, stream));
+  // timing events only when somebody will read them (stats now, or at rtrb_wait)
+  const bool timed = stats_out != nullptr || ctl != nullptr;
+  if (timed) CUDA_TRY(cudaEventRecord(fc.ev0, stream));
   CUDA_TRY(cudaMemsetAsync(fc.d.p, 0, RTRB_FCB_WORDS * sizeof(unsigned long long), stream));
-  CUDA_TRY(cudaMemsetAsync(fc.d.p + RTRB_CNT_N, 0xff, sizeof(unsigned long long), stream));
   const bool partial = !(x0 == 0 && y0 == 0 && x1 == W && y1 == H && world == 1);
   if (partial && !tg.no_fill && tg.hit == r->hit.p && tg.hit) {
     size_t n = (size_t)W * H;
@@ -593,9 +598,9 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     g_launches++;
   }
   if (n_tiles > 0) {
-    CUDA_TRY(cudaEventRecord(fc.evt0, stream));
+    if (timed) CUDA_TRY(cudaEventRecord(fc.evt0, stream));
     CUDA_TRY(strict ? rtrb_launch_trace_pre_strict(P, stack_need, stream) : rtrb_launch_trace_pre_fast(P, stack_need, stream));
-    CUDA_TRY(cudaEventRecord(fc.evt1, stream));
+    if (timed) CUDA_TRY(cudaEventRecord(fc.evt1, stream));
     g_launches++;
     if (!P.fuse_resolve) {
       resolve_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, stream>>>(P);
@@ -655,9 +660,10 @@ int finish_stats(rtrb_renderer* r, FrameCtl& fc, rtrb_stats* stats_out) {
                                  : (uint64_t)fc.px_count * fc.S + (uint64_t)(fc.E > 0 ? c[RTRB_CNT_ADAPTIVE] * (uint64_t)fc.E : 0);
   stats_out->status = st[0];
   stats_out->max_stack = st[1];
-  if (st[0] && c[RTRB_CNT_N] != ~0ull) {
-    stats_out->first_bad_x = (int32_t)(c[RTRB_CNT_N] / (unsigned long long)fc.H);
-    stats_out->first_bad_y = (int32_t)(c[RTRB_CNT_N] % (unsigned long long)fc.H);
+  if (st[0] && c[RTRB_CNT_N] != 0ull) {  // stored complemented so that an all-zero block means "none"
+    const unsigned long long key = ~c[RTRB_CNT_N];
+    stats_out->first_bad_x = (int32_t)(key / (unsigned long long)fc.H);
+    stats_out->first_bad_y = (int32_t)(key % (unsigned long long)fc.H);
   } else {
     stats_out->first_bad_x = stats_out->first_bad_y = -1;
   }
@@ -835,6 +841,16 @@ int rtrb_framebuffer_device_ptr(rtrb_renderer* r, int width, int height, void** 
   int rc = ensure_framebuffers(r, width, height, false, false);
   if (rc) return rc;
   *ptr_out = r->rgba.p;
+  return RTRB_OK;
+}
+
+int rtrb_framebuffer_download(rtrb_renderer* r, int width, int height, uint8_t* rgba_host) {
+  if (!r || !rgba_host || width <= 0 || height <= 0) return fail(RTRB_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(r->device));
+  const size_t bytes = (size_t)width * height * 4;
+  if (r->rgba.n < bytes) return fail(RTRB_ERR_INVALID, "framebuffer is smaller than %dx%d", width, height);
+  CUDA_TRY(cudaMemcpyAsync(rgba_host, r->rgba.p, bytes, cudaMemcpyDeviceToHost, r->copy_stream));
+  CUDA_TRY(cudaStreamSynchronize(r->copy_stream));
   return RTRB_OK;
 }
 

@@ -505,7 +505,8 @@ __device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, 
   }
   if (active && ctx.status) {
     atomicOr(&P.status[0], ctx.status);
-    atomicMin(P.first_bad, (unsigned long long)x * (unsigned long long)P.height + (unsigned long long)y);
+    // smallest x*H + y wins; stored complemented (atomicMax) so the control block can be zero-initialised
+    atomicMax(P.first_bad, ~((unsigned long long)x * (unsigned long long)P.height + (unsigned long long)y));
   }
 }
 

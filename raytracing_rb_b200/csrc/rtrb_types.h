@@ -104,7 +104,7 @@ struct FrameParams {
   uint8_t* rgba;               // [H][W][4] (may be a peer mapping)
   unsigned long long* counters;// RTRB_CNT_* u64 counters
   uint32_t* status;            // [0] status bits, [1] max stack
-  unsigned long long* first_bad;// min over flagged pixels of x*H + y
+  unsigned long long* first_bad;// max over flagged pixels of ~(x*H + y)  (0 = none)
   // adaptive pass
   uint32_t* extra_count;       // number of pixels taking the extra-sample branch
   uint32_t* extra_list;        // [n_tiles*1024] pixel slots (tile k * 1024 + q)

@@ -25,13 +25,14 @@ class Frame:
 
 
 def make_opts(rng_mode=_abi.RNG_CTR, precision=_abi.PREC_DEFAULT, seed=1, window=None, tile_rank=0, tile_world=1,
-              count_detail=False, stream=None, rgba_device_out=None):
+              count_detail=False, stream=None, rgba_device_out=None, skip_outputs=0):
     o = _abi.RenderOpts()
     o.rng_mode, o.precision, o.seed = rng_mode, precision, seed
     if window:
         o.x0, o.y0, o.x1, o.y1 = window
     o.tile_rank, o.tile_world = tile_rank, tile_world
     o.count_detail = 1 if count_detail else 0
+    o.skip_outputs = skip_outputs
     o.stream = stream
     o.rgba_device_out = rgba_device_out
     return o
@@ -107,6 +108,10 @@ class Renderer:
         p = C.c_void_p()
         check(lib().rtrb_framebuffer_device_ptr(self._h, width, height, C.byref(p)))
         return p.value
+
+    def framebuffer_download(self, width, height, out):
+        check(lib().rtrb_framebuffer_download(self._h, width, height, out.ctypes.data))
+        return out
 
     def framebuffer_ipc_export(self, width, height):
         buf = (C.c_uint8 * 64)()
