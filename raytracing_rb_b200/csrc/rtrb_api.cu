@@ -58,6 +58,23 @@ inline H3 hsub(H3 a, H3 b) { return H3{a.x - b.x, a.y - b.y, a.z - b.z}; }
 inline H3 hmul(H3 a, double s) { return H3{a.x * s, a.y * s, a.z * s}; }
 inline void put(double* d, H3 a) { d[0] = a.x; d[1] = a.y; d[2] = a.z; }
 
+// Apex table entry for sphere (C, R) seen from apex A with positional uncertainty rho (see FrameParams).
+// Margins: rounding of v and of the FP32 direction (8 eps |v| on b, hence 16 eps |v|^2 on b^2), the
+// apex uncertainty, and the filter's usual scale term; Kq is rounded DOWN so the test only ever errs
+// towards keeping a sphere.
+float4 apex_entry(const double A[3], double rho, const double C[3], double R, double m_scale) {
+  const double eps = 5.9604644775390625e-8;  // 2^-24
+  const double vx = C[0] - A[0], vy = C[1] - A[1], vz = C[2] - A[2];
+  const double v2 = vx * vx + vy * vy + vz * vz, vlen = sqrt(v2);
+  const double Rp = fabs(R) + rho + 96.0 * eps * (m_scale + vlen) + 8.0 * eps * vlen;
+  const double K = Rp * Rp + 32.0 * eps * v2;
+  const double Kq = v2 - K;
+  float kf = (float)Kq;
+  if ((double)kf > Kq) kf = nextafterf(kf, -INFINITY);
+  if (!(Kq == Kq)) kf = -INFINITY;  // NaN: always survive
+  return make_float4((float)vx, (float)vy, (float)vz, kf);
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -123,6 +140,8 @@ struct rtrb_renderer {
   // FP32 filter view (FAST64)
   DevBuf<float4> cull_sph, cull_pl;
   DevBuf<BvhNode> bvh;
+  DevBuf<float4> light_tab;            // apex tables of the lights (linear-filter scenes)
+  std::vector<double> sph_world;       // (cx, cy, cz, R) in cull_sph[] order, FP64, for the per-frame camera table
   DevBuf<int32_t> sph_index, pl_index;
   DevBuf<DevLightF> lights_f;
   int n_sph = 0, n_pl = 0;
@@ -383,6 +402,18 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
   CUDA_TRY(r->bvh.ensure(std::max<size_t>(1, nodes.size())));
   if (!nodes.empty()) CUDA_TRY(cudaMemcpy(r->bvh.p, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
   r->n_sph = (int)isph.size(); r->n_pl = (int)ipl.size();
+  r->sph_world.clear();
+  for (const BvhBuildSphere& bs : bsph) { for (int k = 0; k < 3; ++k) r->sph_world.push_back(bs.c[k]); r->sph_world.push_back(bs.r); }
+  if (nodes.empty() && !bsph.empty() && (int)bsph.size() <= RTRB_APEX_MAX && s->n_lights > 0) {
+    std::vector<float4> lt((size_t)s->n_lights * bsph.size());
+    for (int l = 0; l < s->n_lights; ++l) {
+      double lm = fmax(fabs(s->lights[l].position[0]), fmax(fabs(s->lights[l].position[1]), fabs(s->lights[l].position[2])));
+      for (size_t k = 0; k < bsph.size(); ++k)
+        lt[(size_t)l * bsph.size() + k] = apex_entry(s->lights[l].position, 0.0, bsph[k].c, bsph[k].r, (double)m_scene + lm);
+    }
+    CUDA_TRY(r->light_tab.ensure(lt.size()));
+    CUDA_TRY(cudaMemcpy(r->light_tab.p, lt.data(), lt.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  }
   r->m_scene = m_scene;
   r->max_distance_f = nextafterf((float)s->max_distance, INFINITY);
   std::vector<DevLightF> lf(s->n_lights);
@@ -572,6 +603,15 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.lights_f = r->lights_f.p; P.n_sph = r->n_sph; P.n_pl = r->n_pl; P.bvh = r->bvh.p;
   P.m_scene = r->m_scene; P.max_distance_f = r->max_distance_f;
   P.use_bvh = r->n_sph > RTRB_BVH_MIN_SPHERES ? 1 : 0;
+  P.light_tab = r->light_tab.p;  // nullptr unless the scene uses the linear filter
+  P.cam_tab_valid = 0;
+  if (!P.use_bvh && r->n_sph > 0 && r->n_sph <= RTRB_APEX_MAX) {
+    const double cm = fmax(fabs(cam->position[0]), fmax(fabs(cam->position[1]), fabs(cam->position[2])));
+    for (int k = 0; k < r->n_sph; ++k)
+      P.cam_tab[k] = apex_entry(cam->position, fabs(cam->aperture_radius), &r->sph_world[4 * (size_t)k],
+                                r->sph_world[4 * (size_t)k + 3], (double)r->m_scene + cm + fabs(cam->aperture_radius));
+    P.cam_tab_valid = 1;
+  }
   P.key0 = (uint32_t)opts.seed; P.key1 = (uint32_t)(opts.seed >> 32);
   P.x0 = x0; P.y0 = y0; P.x1 = x1; P.y1 = y1;
   P.n_tiles = n_tiles; P.stx_count = stx_count; P.tiles = r->tiles.p;
@@ -732,7 +772,7 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
   r->geom.release(); r->mat.release(); r->lights.release(); r->lens_tab.release();
-  r->bvh.release();
+  r->bvh.release(); r->light_tab.release();
   r->cull_sph.release(); r->cull_pl.release(); r->sph_index.release(); r->pl_index.release(); r->lights_f.release(); r->tiles.release(); r->samples.release();
   r->extra_samples.release(); r->rgb.release(); r->extra_list.release(); r->hit.release(); r->rgba.release();
   r->main_ctl.destroy(); r->pipe_ctl[0].destroy(); r->pipe_ctl[1].destroy();

@@ -374,14 +374,24 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
 // ---- SMALL SCENES: linear FP32 scan, no tree (cull_sph[] stays in world_objects order) -------------
 // World#intersect (world.rb:37-59) = FP32 filter over every object + exact test of the survivors.
 __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
-                                                ThreadCtx& ctx) {
+                                                ThreadCtx& ctx, const bool through_lens) {
   Pack8 S;
   S.clear();
   if (P.n_sph > 65535) return closest_hit_scan(P, o, d, bh, ctx);
+  if (through_lens && P.cam_tab_valid) {
+    // primary ray: passes within aperture_radius of the lens centre -> apex table in the constant bank
 #pragma unroll 4
-  for (int k = 0; k < P.n_sph; ++k) {
-    const float4 s = __ldg(&P.cull_sph[k]);
-    if (!sphere_line_misses(s, r)) S.push((uint32_t)k);
+    for (int k = 0; k < P.n_sph; ++k) {
+      const float4 t = P.cam_tab[k];
+      const float b = fmaf(t.z, r.dz, fmaf(t.y, r.dy, t.x * r.dx));
+      if (!(b * b < t.w)) S.push((uint32_t)k);
+    }
+  } else {
+#pragma unroll 4
+    for (int k = 0; k < P.n_sph; ++k) {
+      const float4 s = __ldg(&P.cull_sph[k]);
+      if (!sphere_line_misses(s, r)) S.push((uint32_t)k);
+    }
   }
   if (S.overflow() || P.n_pl > 8) return closest_hit_scan(P, o, d, bh, ctx);
   // pass 1: the smallest certain upper bound; nothing at or beyond max_distance can win (world.rb:39)
@@ -437,7 +447,8 @@ __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3
 // An object the probe ray certainly misses (or certainly meets beyond the light) has factor 0, hence
 // cover exactly 0 (sphere.rb:29,45-53 multiply everything by factor; world_object.rb:43-47), and
 // total - 0 == total, so skipping it leaves the running difference bit-identical.
-__device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
+__device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 target, const DevLight& L, const int light_index,
+                                                  ThreadCtx& ctx) {
   CoverRay c;
   c.target = target;
   c.lp = mk(L.px, L.py, L.pz);
@@ -454,10 +465,21 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
   Pack8 S, Q;
   S.clear();
   Q.clear();
+  if (P.light_tab != nullptr) {
+    // the probe ray's line passes through the light: apex table of this light
+    const float4* tab = P.light_tab + (size_t)light_index * P.n_sph;
 #pragma unroll 4
-  for (int k = 0; k < P.n_sph; ++k) {
-    const float4 s = __ldg(&P.cull_sph[k]);
-    if (!sphere_line_misses(s, r)) S.push((uint32_t)k);
+    for (int k = 0; k < P.n_sph; ++k) {
+      const float4 t = __ldg(&tab[k]);
+      const float b = fmaf(t.z, r.dz, fmaf(t.y, r.dy, t.x * r.dx));
+      if (!(b * b < t.w)) S.push((uint32_t)k);
+    }
+  } else {
+#pragma unroll 4
+    for (int k = 0; k < P.n_sph; ++k) {
+      const float4 s = __ldg(&P.cull_sph[k]);
+      if (!sphere_line_misses(s, r)) S.push((uint32_t)k);
+    }
   }
   for (int k = 0; k < P.n_pl; ++k) {
     float lo, hi;
@@ -497,14 +519,15 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
 // scan wins below ~32 spheres: measured 5.56 vs 6.05 ms on config 3; the BVH wins 5x on config 5).
 template <bool BVH>
 __device__ __forceinline__ int closest_hit_fast(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
-                                                ThreadCtx& ctx) {
+                                                ThreadCtx& ctx, const bool through_lens) {
   if constexpr (BVH) return closest_hit_bvh(P, o, d, r, bh, ctx);
-  else return closest_hit_linear(P, o, d, r, bh, ctx);
+  else return closest_hit_linear(P, o, d, r, bh, ctx, through_lens);
 }
 template <bool BVH>
-__device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
+__device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target, const DevLight& L, const int light_index,
+                                                ThreadCtx& ctx) {
   if constexpr (BVH) return lit_area_bvh(P, target, L, ctx);
-  else return lit_area_linear(P, target, L, ctx);
+  else return lit_area_linear(P, target, L, light_index, ctx);
 }
 
 // World#high_lights match for one light (world.rb:86-93): acos(|cos|) < threshold, filtered in FP32 on
@@ -574,7 +597,7 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
 
     // ---- World#intersect ----
     HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false;
-    const int best_i = closest_hit_fast<BVH>(P, o, d, r, bh, ctx);
+    const int best_i = closest_hit_fast<BVH>(P, o, d, r, bh, ctx, is_first);
     if (best_i < 0) return;
     if (is_first) *primary_hit = best_i;
     RTRB_COUNT(ctx, RTRB_CNT_HITS);
@@ -674,7 +697,7 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
     for (int l = 0; l < P.n_lights; ++l) {
       const DevLight& L = P.lights[l];
       ctx.shadow++;
-      const double area = lit_area_fast<BVH>(P, shade_from, L, ctx);
+      const double area = lit_area_fast<BVH>(P, shade_from, L, l, ctx);
       if (area > 0) {
         double w = rb_pow(area, P.soft_shadow_exponent);
         if (P.n_lights != 1) w = w / (double)P.n_lights;  // x / 1.0 == x

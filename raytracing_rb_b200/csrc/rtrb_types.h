@@ -15,6 +15,7 @@
 #define RTRB_MAX_LIGHTS 64
 #define RTRB_SUPER 32                 // super-tile edge in pixels (tile partition unit across GPUs)
 #define RTRB_SUPER_PIXELS (RTRB_SUPER * RTRB_SUPER)
+#define RTRB_APEX_MAX 32              // linear-filter scenes (<= 32 spheres) get apex tables, see FrameParams
 
 struct DevGeom {      // 64 B
   double px, py, pz;  // sphere centre / plane point
@@ -86,6 +87,13 @@ struct FrameParams {
   const struct BvhNode* bvh;   // sphere BVH over cull_sph[] (rtrb_bvh.h); node 0 = root
   int32_t n_sph, n_pl;
   int32_t use_bvh, pad_bvh;    // > RTRB_BVH_MIN_SPHERES spheres: BVH kernels; else the linear-scan kernels
+  // Apex tables (linear-filter scenes only): rays that pass through a known point A — primary rays
+  // through the lens centre (within aperture_radius), shadow probes through their light — test sphere k
+  // with b = v.u, survive unless b*b < Kq, where (v, Kq) = (C - A, |v|^2 - (R + margins)^2 - slack)
+  // is precomputed per (apex, sphere).  cam_tab lives in the kernel parameters (constant bank).
+  float4 cam_tab[RTRB_APEX_MAX];
+  const float4* light_tab;     // [n_lights][n_sph] or nullptr
+  int32_t cam_tab_valid, pad_tab;
   float m_scene;               // max over spheres of |C|_inf + R  (error-bound scale)
   float max_distance_f;        // max_distance rounded up to float
   // rng
