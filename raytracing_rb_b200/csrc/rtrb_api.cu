@@ -610,6 +610,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     for (int k = 0; k < r->n_sph; ++k)
       P.cam_tab[k] = apex_entry(cam->position, fabs(cam->aperture_radius), &r->sph_world[4 * (size_t)k],
                                 r->sph_world[4 * (size_t)k + 3], (double)r->m_scene + cm + fabs(cam->aperture_radius));
+    for (int k = r->n_sph; k < RTRB_APEX_MAX; ++k) P.cam_tab[k] = make_float4(0.0f, 0.0f, 0.0f, INFINITY);  // never survives
     P.cam_tab_valid = 1;
   }
   P.key0 = (uint32_t)opts.seed; P.key1 = (uint32_t)(opts.seed >> 32);

@@ -373,36 +373,59 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
 
 // ---- SMALL SCENES: linear FP32 scan, no tree (cull_sph[] stays in world_objects order) -------------
 // World#intersect (world.rb:37-59) = FP32 filter over every object + exact test of the survivors.
+// Survivors of the linear filter are a 32-bit mask over cull_sph[] (n_sph <= RTRB_APEX_MAX = 32 here),
+// bit k = sphere k in world_objects order; the hot loop is branch-free.
+__device__ __forceinline__ uint32_t line_survivors_generic(const FrameParams& P, const CullRay& r) {
+  uint32_t m = 0u;
+#pragma unroll 4
+  for (int k = 0; k < P.n_sph; ++k) {
+    const float4 s = __ldg(&P.cull_sph[k]);
+    m |= (sphere_line_misses(s, r) ? 0u : 1u) << k;
+  }
+  return m;
+}
+// Apex-table form: b = v.u, survive unless b*b < Kq (NaN survives).  Padding entries have Kq = +inf.
+__device__ __forceinline__ uint32_t apex_test(const float4 t, const CullRay& r) {
+  const float b = fmaf(t.z, r.dz, fmaf(t.y, r.dy, t.x * r.dx));
+  return (b * b < t.w) ? 0u : 1u;
+}
+__device__ __forceinline__ uint32_t line_survivors_camera(const FrameParams& P, const CullRay& r) {
+  // constant indices: the table is read straight from the constant bank, eight spheres per uniform branch
+  uint32_t m = 0u;
+#pragma unroll
+  for (int blk = 0; blk < RTRB_APEX_MAX / 8; ++blk) {
+    if (blk * 8 < P.n_sph) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m |= apex_test(P.cam_tab[blk * 8 + j], r) << (blk * 8 + j);
+    }
+  }
+  return m;
+}
+__device__ __forceinline__ uint32_t line_survivors_light(const FrameParams& P, const int light_index, const CullRay& r) {
+  const float4* tab = P.light_tab + (size_t)light_index * P.n_sph;
+  uint32_t m = 0u;
+#pragma unroll 4
+  for (int k = 0; k < P.n_sph; ++k) m |= apex_test(__ldg(&tab[k]), r) << k;
+  return m;
+}
+
+// World#intersect (world.rb:37-59) = FP32 filter over every object + exact test of the survivors.
 __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx, const bool through_lens) {
-  Pack8 S;
-  S.clear();
-  if (P.n_sph > 65535) return closest_hit_scan(P, o, d, bh, ctx);
-  if (through_lens && P.cam_tab_valid) {
-    // primary ray: passes within aperture_radius of the lens centre -> apex table in the constant bank
-#pragma unroll 4
-    for (int k = 0; k < P.n_sph; ++k) {
-      const float4 t = P.cam_tab[k];
-      const float b = fmaf(t.z, r.dz, fmaf(t.y, r.dy, t.x * r.dx));
-      if (!(b * b < t.w)) S.push((uint32_t)k);
-    }
-  } else {
-#pragma unroll 4
-    for (int k = 0; k < P.n_sph; ++k) {
-      const float4 s = __ldg(&P.cull_sph[k]);
-      if (!sphere_line_misses(s, r)) S.push((uint32_t)k);
-    }
-  }
-  if (S.overflow() || P.n_pl > 8) return closest_hit_scan(P, o, d, bh, ctx);
-  // pass 1: the smallest certain upper bound; nothing at or beyond max_distance can win (world.rb:39)
+  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > 8) return closest_hit_scan(P, o, d, bh, ctx);
+  const uint32_t mask = (through_lens && P.cam_tab_valid) ? line_survivors_camera(P, r) : line_survivors_generic(P, r);
+  // pass 1 (only when something can be pruned): the smallest certain upper bound; nothing at or beyond
+  // max_distance can win (world.rb:39)
   float best_hi = P.max_distance_f;
-  for (int c = 0; c < S.n; ++c) {
-    float lo, hi;
-    if (classify_sphere(__ldg(&P.cull_sph[S.get(c)]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
-  }
-  for (int k = 0; k < P.n_pl; ++k) {
-    float lo, hi;
-    if (classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
+  if (mask != 0u || P.n_pl > 1) {
+    for (uint32_t m = mask; m != 0u; m &= m - 1u) {
+      float lo, hi;
+      if (classify_sphere(__ldg(&P.cull_sph[__ffs(m) - 1]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
+    }
+    for (int k = 0; k < P.n_pl; ++k) {
+      float lo, hi;
+      if (classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
+    }
   }
   // pass 2: exact FP64 evaluation of whatever can still win; (distance, index) lexicographic order
   // reproduces the strict `<` scan in world_objects order.
@@ -411,8 +434,8 @@ __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3
   bool have_dn = false;
   double d_r = 0;
   d3 dn = mk(0, 0, 0);
-  for (int c = 0; c < S.n; ++c) {
-    const uint32_t k = S.get(c);
+  for (uint32_t m = mask; m != 0u; m &= m - 1u) {
+    const int k = __ffs(m) - 1;
     float lo, hi;
     const int kind = classify_sphere(__ldg(&P.cull_sph[k]), r, lo, hi);
     if (kind == 0 || !(lo <= best_hi)) continue;
@@ -461,43 +484,26 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
     const float lx = (float)c.lt.x, ly = (float)c.lt.y, lz = (float)c.lt.z;
     far = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) * 1.00001f + 2.0f * r.E;
   }
-  if (P.n_sph > 65535 || P.n_pl > 65535) return lit_area(P, target, L, ctx);
-  Pack8 S, Q;
-  S.clear();
-  Q.clear();
-  if (P.light_tab != nullptr) {
-    // the probe ray's line passes through the light: apex table of this light
-    const float4* tab = P.light_tab + (size_t)light_index * P.n_sph;
-#pragma unroll 4
-    for (int k = 0; k < P.n_sph; ++k) {
-      const float4 t = __ldg(&tab[k]);
-      const float b = fmaf(t.z, r.dz, fmaf(t.y, r.dy, t.x * r.dx));
-      if (!(b * b < t.w)) S.push((uint32_t)k);
-    }
-  } else {
-#pragma unroll 4
-    for (int k = 0; k < P.n_sph; ++k) {
-      const float4 s = __ldg(&P.cull_sph[k]);
-      if (!sphere_line_misses(s, r)) S.push((uint32_t)k);
-    }
-  }
+  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > 32) return lit_area(P, target, L, ctx);
+  // the probe ray's line passes through the light: apex table of this light when there is one
+  uint32_t sm = (P.light_tab != nullptr) ? line_survivors_light(P, light_index, r) : line_survivors_generic(P, r);
+  uint32_t qm = 0u;
   for (int k = 0; k < P.n_pl; ++k) {
     float lo, hi;
     const int kind = classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi);
-    if (kind != 0 && !(lo > far)) Q.push((uint32_t)k);
+    if (kind != 0 && !(lo > far)) qm |= 1u << k;
   }
-  if (S.overflow() || Q.overflow()) return lit_area(P, target, L, ctx);
   double total = 1;
   bool have_n = false;
-  int cs = 0, cq = 0;
-  // merge the two survivor lists (each ascending in world_objects index) so covers subtract in order
-  while (cs < S.n || cq < Q.n) {
-    const int is = cs < S.n ? P.sph_index[S.get(cs)] : 0x7fffffff;
-    const int iq = cq < Q.n ? P.pl_index[Q.get(cq)] : 0x7fffffff;
+  // merge the two survivor sets (each ascending in world_objects index) so covers subtract in order
+  while (sm != 0u || qm != 0u) {
+    const int ks = sm ? __ffs(sm) - 1 : -1, kq = qm ? __ffs(qm) - 1 : -1;
+    const int is = ks >= 0 ? P.sph_index[ks] : 0x7fffffff;
+    const int iq = kq >= 0 ? P.pl_index[kq] : 0x7fffffff;
     if (is < iq) {
-      const uint32_t k = S.get(cs++);
+      sm &= sm - 1u;
       float lo, hi;
-      const int kind = classify_sphere(__ldg(&P.cull_sph[k]), r, lo, hi);
+      const int kind = classify_sphere(__ldg(&P.cull_sph[ks]), r, lo, hi);
       if (kind == 0 || lo > far) continue;
       if (!have_n) {
         c.lt_r = norm(c.lt);
@@ -507,7 +513,7 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
       RTRB_COUNT(ctx, RTRB_CNT_EXACT);
       total -= cover_object_exact(P.geom[is], c, L.radius, ctx);
     } else {
-      cq++;
+      qm &= qm - 1u;
       RTRB_COUNT(ctx, RTRB_CNT_EXACT);
       total -= cover_object_exact(P.geom[iq], c, L.radius, ctx);
     }
