@@ -700,7 +700,7 @@ int finish_stats(rtrb_renderer* r, FrameCtl& fc, rtrb_stats* stats_out) {
   stats_out->samples = fc.detail ? c[RTRB_CNT_SAMPLES]
                                  : (uint64_t)fc.px_count * fc.S + (uint64_t)(fc.E > 0 ? c[RTRB_CNT_ADAPTIVE] * (uint64_t)fc.E : 0);
   stats_out->status = st[0];
-  stats_out->max_stack = st[1];
+  stats_out->max_stack = st[1] > 1u ? st[1] : (c[RTRB_CNT_RAYS] ? 1u : 0u);  // blocks only report depths > 1
   if (st[0] && c[RTRB_CNT_N] != 0ull) {  // stored complemented so that an all-zero block means "none"
     const unsigned long long key = ~c[RTRB_CNT_N];
     stats_out->first_bad_x = (int32_t)(key / (unsigned long long)fc.H);

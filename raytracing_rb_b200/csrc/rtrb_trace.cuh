@@ -485,15 +485,25 @@ __device__ __forceinline__ bool decode_pixel(const FrameParams& P, uint32_t slot
 }
 
 __device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, int x, int y, bool active) {
-  // warp-aggregate the two lean counters, then one atomic per warp
+  // warp totals by hardware reduction (REDUX), block totals through shared memory, then ONE atomic
+  // per block and counter: 65 K warps hammering three addresses would serialise in the L2 atomic unit
   const unsigned full = 0xffffffffu;
   const uint32_t rays = __reduce_add_sync(full, ctx.rays), shadow = __reduce_add_sync(full, ctx.shadow),
                  ms = __reduce_max_sync(full, ctx.max_stack);
   const int lane = threadIdx.x & 31;
+  __shared__ unsigned int blk[3];
+  if (threadIdx.x == 0) { blk[0] = 0u; blk[1] = 0u; blk[2] = 0u; }
+  __syncthreads();
   if (lane == 0) {
-    if (rays) atomicAdd(&P.counters[RTRB_CNT_RAYS], (unsigned long long)rays);
-    if (shadow) atomicAdd(&P.counters[RTRB_CNT_SHADOW], (unsigned long long)shadow);
-    atomicMax(&P.status[1], ms);
+    if (rays) atomicAdd(&blk[0], rays);
+    if (shadow) atomicAdd(&blk[1], shadow);
+    atomicMax(&blk[2], ms);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (blk[0]) atomicAdd(&P.counters[RTRB_CNT_RAYS], (unsigned long long)blk[0]);
+    if (blk[1]) atomicAdd(&P.counters[RTRB_CNT_SHADOW], (unsigned long long)blk[1]);
+    if (blk[2] > 1u) atomicMax(&P.status[1], blk[2]);  // 1 (just the root) is the host-side default
   }
   if (ctx.detail) {
 #pragma unroll
