@@ -146,7 +146,9 @@ def run_reference(args, rank, world_size):
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "host": "CPU only", "ruby_present": ruby},
+        "config": {"workload": name + "; one step = a batch of %d frames (camera dolly)" % args.frames_per_step,
+                   "frames_per_step": args.frames_per_step, "host": "CPU only (one frame of the batch per step)",
+                   "ruby_present": ruby},
         "frames_per_s_equiv": args.steps / dt * (ww / W),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -270,7 +272,8 @@ def run_ours(args, rank, local_rank, world_size):
     cam_bytes = C.sizeof(_abi.CameraDesc) + C.sizeof(_abi.RenderOpts)
     e2e_opts = make_opts(seed=1, precision=precision)
     if world_size == 1:
-        bufs = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+        DEPTH = 3  # frames in flight (the library allows 4)
+        bufs = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(DEPTH)]
     elif rank == 0:
         host_batch = torch.empty((H * B, W, 4), dtype=torch.uint8).pin_memory().numpy()
 
@@ -279,14 +282,15 @@ def run_ours(args, rank, local_rank, world_size):
         renders while frame i crosses PCIe).  N > 1: every rank renders its tiles of the B frames into
         rank 0's frame slots, then rank 0 copies the batch to the host."""
         if world_size == 1:
-            prev, i = None, 0
+            pending, i = [], 0
             for _ in range(n_steps):
                 for f in range(B):
-                    t = r.submit(cams[f], bufs[i & 1], e2e_opts)
-                    if prev is not None:
-                        r.wait(prev)
-                    prev, i = t, i + 1
-            r.wait(prev)
+                    if len(pending) == DEPTH:
+                        r.wait(pending.pop(0))
+                    pending.append(r.submit(cams[f], bufs[i % DEPTH], e2e_opts))
+                    i += 1
+            for t in pending:
+                r.wait(t)
         else:
             for _ in range(n_steps):
                 step()
@@ -317,7 +321,7 @@ def run_ours(args, rank, local_rank, world_size):
             "frames_per_s": args.steps * B / (total_ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": cam_bytes * B,
                     "d2h_bytes_per_step": frame_bytes * B, "frames_per_s": args.steps * B / e2e_s,
-                    "api": "rtrb_submit/rtrb_wait (2 frames in flight, pinned host buffers)" if world_size == 1 else
+                    "api": "rtrb_submit/rtrb_wait (3 frames in flight, pinned host buffers)" if world_size == 1 else
                            "rtrb_render_device per rank into rank 0's frame slots + barrier + rtrb_framebuffer_download"},
             "gpu_launches": int(launches_total),
             "clocks": clocks,
@@ -328,7 +332,7 @@ def run_ours(args, rank, local_rank, world_size):
             achieved = flops_frame / (trace_ms * 1e-3) / 1e12
             line["roofline"] = {
                 "bound": "fp64", "kernel": "trace_pre_fast_kernel", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
-                "frac": achieved / peak64 if peak64 else None, "traffic": None,
+                "frac": achieved / peak64 if peak64 else None, "traffic": ncu_traffic_bytes(),
                 "peak_source": "measured in this job: dependent-free DFMA microbenchmark (rtrb_measure_fma_peak)",
                 "peak_fp32": peak32, "algorithmic_flops_per_launch": flops_frame, "kernel_ms": trace_ms,
                 "hbm": {"algorithmic_bytes_per_launch": frame_bytes, "peak_gbs": measured_hbm_gbs(),
@@ -339,6 +343,16 @@ def run_ours(args, rank, local_rank, world_size):
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the trace kernel, per launch, from the committed
+    `ncu --set full` capture of this workload (profiles/r1_traffic.json); None when absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def measured_hbm_gbs():

@@ -199,8 +199,9 @@ int rtrb_render(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
 
 /* Pipelined form of rtrb_render for frame sequences: rtrb_submit launches the frame and queues its
  * device->host copy into rgba_host (pinned memory recommended) on a separate copy stream, then
- * returns; rtrb_wait blocks until that frame's bytes and stats are in host memory.  Two frames may be
- * in flight per renderer, so frame i+1 renders while frame i crosses PCIe.  RGBA8 only. */
+ * returns; rtrb_wait blocks until that frame's bytes and stats are in host memory.  Up to four frames
+ * may be in flight per renderer (tickets are consecutive integers; wait for them in order), so
+ * later frames render while earlier ones cross PCIe.  RGBA8 only. */
 int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts, uint8_t* rgba_host,
                 int* ticket_out);
 int rtrb_wait(rtrb_renderer* r, int ticket, rtrb_stats* stats_out);

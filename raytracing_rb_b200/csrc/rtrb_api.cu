@@ -97,6 +97,7 @@ struct DevBuf {
 // u64 words: [0, RTRB_CNT_N) counters | [N] first_bad | [N+1, N+2] work claims | [N+3] = {status, max_stack}
 // | [N+4] = {extra_count, pad}
 #define RTRB_FCB_WORDS (RTRB_CNT_N + 5)
+#define RTRB_PIPE_SLOTS 4  // frames that may be in flight between rtrb_submit and rtrb_wait
 struct FrameCtl {
   DevBuf<unsigned long long> d;
   unsigned long long* h = nullptr;  // pinned host mirror
@@ -128,7 +129,7 @@ struct rtrb_renderer {
   int device = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   FrameCtl main_ctl;       // synchronous calls
-  FrameCtl pipe_ctl[2];    // rtrb_submit / rtrb_wait double buffering
+  FrameCtl pipe_ctl[RTRB_PIPE_SLOTS];  // rtrb_submit / rtrb_wait frame slots
   bool pipe_ready = false;
   unsigned next_ticket = 0;
   // baked scene
@@ -776,7 +777,8 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   r->bvh.release(); r->light_tab.release();
   r->cull_sph.release(); r->cull_pl.release(); r->sph_index.release(); r->pl_index.release(); r->lights_f.release(); r->tiles.release(); r->samples.release();
   r->extra_samples.release(); r->rgb.release(); r->extra_list.release(); r->hit.release(); r->rgba.release();
-  r->main_ctl.destroy(); r->pipe_ctl[0].destroy(); r->pipe_ctl[1].destroy();
+  r->main_ctl.destroy();
+  for (int i = 0; i < RTRB_PIPE_SLOTS; ++i) r->pipe_ctl[i].destroy();
   for (uint8_t* t : r->textures) cudaFree(t);
   if (r->stream) cudaStreamDestroy(r->stream);
   if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
@@ -829,15 +831,15 @@ int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   if (!r || !cam || !rgba_host || !ticket_out) return fail(RTRB_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(r->device));
   if (!r->pipe_ready) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < RTRB_PIPE_SLOTS; ++i) {
       cudaError_t e = (cudaError_t)r->pipe_ctl[i].init();
       if (e != cudaSuccess) return fail(RTRB_ERR_CUDA, "pipeline slot init failed: %s", cudaGetErrorString(e));
     }
     r->pipe_ready = true;
   }
   const unsigned ticket = r->next_ticket;
-  FrameCtl& fc = r->pipe_ctl[ticket & 1u];
-  if (fc.in_flight) return fail(RTRB_ERR_INVALID, "two frames are already in flight: call rtrb_wait first");
+  FrameCtl& fc = r->pipe_ctl[ticket % RTRB_PIPE_SLOTS];
+  if (fc.in_flight) return fail(RTRB_ERR_INVALID, "%d frames are already in flight: call rtrb_wait first", RTRB_PIPE_SLOTS);
   const size_t bytes = (size_t)cam->width * cam->height * 4;
   if (cam->width > 0 && cam->height > 0 && fc.rgba.n < bytes) {
     CUDA_TRY(fc.rgba.ensure(bytes));
@@ -868,7 +870,7 @@ int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
 
 int rtrb_wait(rtrb_renderer* r, int ticket, rtrb_stats* stats_out) {
   if (!r || !r->pipe_ready) return fail(RTRB_ERR_INVALID, "nothing submitted");
-  FrameCtl& fc = r->pipe_ctl[(unsigned)ticket & 1u];
+  FrameCtl& fc = r->pipe_ctl[(unsigned)ticket % RTRB_PIPE_SLOTS];
   if (!fc.in_flight) return fail(RTRB_ERR_INVALID, "ticket %d is not in flight", ticket);
   CUDA_TRY(cudaSetDevice(r->device));
   CUDA_TRY(cudaEventSynchronize(fc.copied));

@@ -14,6 +14,7 @@ ap.add_argument("--precision", default="fast64")
 ap.add_argument("--width", type=int, default=0)
 ap.add_argument("--height", type=int, default=0)
 ap.add_argument("--spp", type=int, default=0)
+ap.add_argument("--lean", action="store_true", help="RGBA8 only (what bench.py renders): skip the optional float RGB / hit-id frames")
 a = ap.parse_args()
 kw = {}
 if a.width:
@@ -24,6 +25,6 @@ w, c = scenes.build(a.config, **kw)
 cam = Camera(World(w), c)
 prec = PREC_STRICT if a.precision == "strict" else PREC_FAST64
 for i in range(a.frames):
-    st, _ = cam.renderer().render_device(cam.camera_desc(), make_opts(seed=1, precision=prec))
+    st, _ = cam.renderer().render_device(cam.camera_desc(), make_opts(seed=1, precision=prec, skip_outputs=3 if a.lean else 0))
     print("frame %d: device %.3f ms trace %.3f ms rays %d shadow %d" % (i, st["device_ms"], st["trace_ms"], st["rays"],
                                                                       st["shadow_queries"]))
