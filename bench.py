@@ -9,9 +9,13 @@ ground plane + 16 spheres, hard shadows, 1 spp, no recursion).  Metric: Mrays/s 
 traced rays (work-stack items passing the cut at ray_tracer.rb:52) + shadow queries (lit_area calls
 from local_lights, world.rb:75), SURVEY.md 8d.
 
-For N > 1 (torchrun, one rank per GPU) the frame's 32x32-pixel super-tiles are dealt round-robin
-to the ranks and every rank's resolve kernel writes its pixels straight into rank 0's framebuffer
-through a CUDA-IPC peer mapping over NVLink: no collective on the data path (strong scaling).
+A step is a batch of --frames-per-step frames PER GPU (a camera dolly).  For N > 1 (torchrun, one
+rank per GPU) the batch's frames are the dealing unit: config 2 is a 0.12 ms frame, far too small to
+cut into tiles per GPU, so rank r renders frames [r*B, (r+1)*B) whole and they are gathered into rank
+0's frame slots through a CUDA-IPC peer mapping over NVLink - by direct peer stores from the trace
+kernel (--gather store) or by the copy engine behind the kernel (--gather copy).  No collective on the
+data path; per-GPU work is fixed as N grows (weak scaling).  Tile partitioning of ONE heavy frame
+(config 5) is `--tile-split` (strong scaling of a single frame).
 """
 import argparse
 import ctypes as C
@@ -156,13 +160,14 @@ def run_reference(args, rank, world_size):
     print(json.dumps(line))
 
 
-def batch_cameras(world, cdoc, n):
-    """The step's batch: n frames of the workload with the camera dollying sideways (a short fly-by)."""
+def batch_cameras(world, cdoc, n, first=0):
+    """Frames [first, first+n) of the fly-by: the workload's camera dollying sideways, 0.02 per frame
+    (wrapping every 64 frames so every rank's share of a large batch shows the same scene content)."""
     from raytracing_rb_b200 import Camera
     cams = []
-    for f in range(n):
+    for f in range(first, first + n):
         c = Camera(world, cdoc).camera_desc()
-        c.position[1] = c.position[1] + 0.02 * f
+        c.position[1] = c.position[1] + 0.02 * (f % 64)
         cams.append(c)
     return cams
 
@@ -181,30 +186,48 @@ def run_ours(args, rank, local_rank, world_size):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     precision = PREC_STRICT if args.precision == "strict" else PREC_FAST64
+    fmt = _abi.FMT_RGB8 if args.pixel_format == "rgb8" else _abi.FMT_RGBA8
+    bpp = 3 if fmt == _abi.FMT_RGB8 else 4
     world, cdoc, name = workload(args.config, args.small)
+    if args.spp:
+        cdoc = dict(cdoc, pre_sample_times=args.spp, max_sample_times=args.spp)
     B = max(1, args.frames_per_step)
-    cams = batch_cameras(world, cdoc, B)
+    tile_split = bool(args.tile_split) and world_size > 1
+    # frames this rank renders per step, and the slot each lands in inside rank 0's framebuffer
+    if tile_split:
+        cams = batch_cameras(world, cdoc, B)            # every rank: its tiles of the same B frames
+        slots = list(range(B))
+        n_slots = B
+    else:
+        cams = batch_cameras(world, cdoc, B, rank * B)  # rank r: frames [r*B, (r+1)*B), whole
+        slots = [rank * B + f for f in range(B)]
+        n_slots = B * world_size
     W, H = cams[0].width, cams[0].height
-    frame_bytes = W * H * 4
+    slot_bytes = W * H * 4           # slots are sized for RGBA8 whatever the format
+    frame_bytes = W * H * bpp
     r = Renderer(world.to_scene_desc(), local_rank)
 
-    # ---- where the pixels go: B frame slots in rank 0's framebuffer (a peer mapping for the others) ----
+    # ---- where the pixels go: frame slots in rank 0's framebuffer (a peer mapping for the others) ----
     if rank == 0:
-        base_ptr = r.framebuffer_ptr(W, H * B)
+        base_ptr = r.framebuffer_ptr(W, H * n_slots)
     if world_size > 1:
         hbuf = torch.zeros(64, dtype=torch.uint8, device="cuda")
         if rank == 0:
-            hbuf.copy_(torch.frombuffer(bytearray(r.framebuffer_ipc_export(W, H * B)), dtype=torch.uint8))
+            hbuf.copy_(torch.frombuffer(bytearray(r.framebuffer_ipc_export(W, H * n_slots)), dtype=torch.uint8))
         dist.broadcast(hbuf, 0)
         if rank != 0:
             base_ptr = ipc_open(local_rank, bytes(hbuf.cpu().numpy().tobytes()))
+    use_copy = (not tile_split) and world_size > 1 and rank != 0 and args.gather == "copy"
+    local_ptr = r.framebuffer_ptr(W, H * B) if use_copy else None
     stream = torch.cuda.Stream()  # a real (non-NULL) stream: NULL means "the renderer's own stream" in the C ABI
     torch.cuda.set_stream(stream)
 
     def opts(f, detail=False, prec=None):
-        return make_opts(seed=1, precision=precision if prec is None else prec, tile_rank=rank, tile_world=world_size,
-                         count_detail=detail, stream=stream.cuda_stream, rgba_device_out=base_ptr + f * frame_bytes,
-                         skip_outputs=_abi.SKIP_RGB | _abi.SKIP_HIT)
+        out = (local_ptr + f * slot_bytes) if use_copy else (base_ptr + slots[f] * slot_bytes)
+        return make_opts(seed=1, precision=precision if prec is None else prec,
+                         tile_rank=rank if tile_split else 0, tile_world=world_size if tile_split else 1,
+                         count_detail=detail, stream=stream.cuda_stream, rgba_device_out=out,
+                         skip_outputs=_abi.SKIP_RGB | _abi.SKIP_HIT, pixel_format=fmt)
 
     def barrier():
         torch.cuda.synchronize()
@@ -216,10 +239,13 @@ def run_ours(args, rank, local_rank, world_size):
     # The algorithmic (brute-force) operation counts come from the STRICT kernel's detailed counters:
     # FAST64 produces the same frames with fewer executed tests, which must not shrink the numerator.
     flops_batch, rays_batch = 0, 0
-    for f in range(B):
-        st, _ = r.render_device(cams[f], opts(f, True, PREC_STRICT))
+    n_count = B if not args.count_one else 1
+    for f in range(n_count):
+        st, _ = r.render_device(cams[f], opts(f, True, PREC_STRICT if not args.count_fast else None))
         flops_batch += algorithmic_flops(st)
         rays_batch += st["rays"] + st["shadow_queries"]
+    if n_count != B:  # heavy frames (config 5): one frame counted, the batch is B copies of its cost
+        flops_batch, rays_batch = flops_batch * B, rays_batch * B
     peak64 = measure_fma_peak(local_rank, True) if rank == 0 else 0.0
     peak32 = measure_fma_peak(local_rank, False) if rank == 0 else 0.0
 
@@ -229,6 +255,10 @@ def run_ours(args, rank, local_rank, world_size):
     def step():
         for f in range(B):
             r.render_device(cams[f], step_opts[f], want_stats=False)
+            if use_copy:  # copy engine carries the finished frame to rank 0 while the next one renders
+                r.peer_push(local_ptr + f * slot_bytes, base_ptr + slots[f] * slot_bytes, frame_bytes, stream.cuda_stream)
+        if use_copy:
+            r.peer_push_join(stream.cuda_stream)  # the step ends when its last frame has landed
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -257,46 +287,37 @@ def run_ours(args, rank, local_rank, world_size):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     total_ms = float(step_ms.sum().item())
     rays_total, flops_total, launches_total = (float(x) for x in tot.tolist())
+    frames_total = n_slots  # frames finished per step by the whole job
     value = rays_total * args.steps / (total_ms * 1e-3) / 1e6
 
     # ---- dominant kernel alone (trace over the pre samples): library-side CUDA events, cold L2 ----
     tr = []
     for k in range(min(args.steps, 10)):
-        for f in range(B):
+        for f in range(B if not args.count_one else 1):
             flush.zero_()
             st, _ = r.render_device(cams[f], opts(f))
             tr.append(st["trace_ms"])
     trace_ms = float(np.mean(tr))
 
     # ---- e2e: the public frame call with HOST buffers (pinned), copies inside the timed region ----
+    # Every rank delivers the frames it rendered to its own pinned host buffers over its own PCIe link
+    # through the pipelined frame API (frame i+1 renders while frame i crosses PCIe).
     cam_bytes = C.sizeof(_abi.CameraDesc) + C.sizeof(_abi.RenderOpts)
-    e2e_opts = make_opts(seed=1, precision=precision)
-    if world_size == 1:
-        DEPTH = 3  # frames in flight (the library allows 4)
-        bufs = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(DEPTH)]
-    elif rank == 0:
-        host_batch = torch.empty((H * B, W, 4), dtype=torch.uint8).pin_memory().numpy()
+    e2e_opts = make_opts(seed=1, precision=precision, pixel_format=fmt,
+                         tile_rank=rank if tile_split else 0, tile_world=world_size if tile_split else 1)
+    DEPTH = 3  # frames in flight (the library allows 4)
+    bufs = [torch.empty((H, W, bpp), dtype=torch.uint8).pin_memory().numpy() for _ in range(DEPTH)]
 
     def e2e_run(n_steps):
-        """N == 1: the pipelined frame API (rtrb_submit / rtrb_wait, two frames in flight: frame i+1
-        renders while frame i crosses PCIe).  N > 1: every rank renders its tiles of the B frames into
-        rank 0's frame slots, then rank 0 copies the batch to the host."""
-        if world_size == 1:
-            pending, i = [], 0
-            for _ in range(n_steps):
-                for f in range(B):
-                    if len(pending) == DEPTH:
-                        r.wait(pending.pop(0))
-                    pending.append(r.submit(cams[f], bufs[i % DEPTH], e2e_opts))
-                    i += 1
-            for t in pending:
-                r.wait(t)
-        else:
-            for _ in range(n_steps):
-                step()
-                barrier()  # all ranks' tiles have landed in rank 0's frame slots
-                if rank == 0:
-                    r.framebuffer_download(W, H * B, host_batch)
+        pending, i = [], 0
+        for _ in range(n_steps):
+            for f in range(B):
+                if len(pending) == DEPTH:
+                    r.wait(pending.pop(0))
+                pending.append(r.submit(cams[f], bufs[i % DEPTH], e2e_opts))
+                i += 1
+        for t in pending:
+            r.wait(t)
     e2e_run(1)
     barrier()
     t0 = time.perf_counter()
@@ -309,36 +330,43 @@ def run_ours(args, rank, local_rank, world_size):
     e2e_value = rays_total * args.steps / e2e_s / 1e6
 
     if rank == 0:
+        if tile_split:
+            how = "32x32 px super-tiles of every frame dealt round-robin over ranks, peer stores into rank 0's framebuffer"
+        elif world_size > 1:
+            how = ("whole frames dealt to ranks (rank r renders frames [r*B, (r+1)*B)), gathered into rank 0's frame slots by " +
+                   ("the copy engine over NVLink (rtrb_peer_push)" if args.gather == "copy" else "direct peer stores from the trace kernel"))
+        else:
+            how = "single GPU"
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name + "; one step = a batch of %d frames (camera dolly)" % B,
-                       "frames_per_step": B, "precision_mode": args.precision, "rays_per_step": rays_total,
+            "scaling": "strong" if tile_split else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name + "; one step = a batch of %d frames per GPU (camera dolly)" % B,
+                       "frames_per_step": frames_total, "frames_per_step_per_gpu": B, "precision_mode": args.precision,
+                       "pixel_format": args.pixel_format, "rays_per_step": rays_total,
                        "l2": "flushed between timed steps (256 MiB write)",
-                       "tiles": "32x32 px super-tiles dealt round-robin over ranks, peer stores into rank 0's framebuffer",
-                       "rng": "philox4x32-10 counter, seed 1"},
-            "frames_per_s": args.steps * B / (total_ms * 1e-3),
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": cam_bytes * B,
-                    "d2h_bytes_per_step": frame_bytes * B, "frames_per_s": args.steps * B / e2e_s,
-                    "api": "rtrb_submit/rtrb_wait (3 frames in flight, pinned host buffers)" if world_size == 1 else
-                           "rtrb_render_device per rank into rank 0's frame slots + barrier + rtrb_framebuffer_download"},
+                       "multi_gpu": how, "rng": "philox4x32-10 counter, seed 1"},
+            "frames_per_s": args.steps * frames_total / (total_ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": cam_bytes * frames_total,
+                    "d2h_bytes_per_step": frame_bytes * frames_total if not tile_split else frame_bytes * B * world_size,
+                    "frames_per_s": args.steps * frames_total / e2e_s,
+                    "api": "rtrb_submit/rtrb_wait per rank (%d frames in flight, pinned host buffers, %s)" % (DEPTH, args.pixel_format)},
             "gpu_launches": int(launches_total),
             "clocks": clocks,
             "wall_s_timed_region": wall,
         }
+        flops_frame = flops_batch / B
+        achieved = flops_frame / (trace_ms * 1e-3) / 1e12
+        line["roofline"] = {
+            "bound": "fp64", "kernel": "trace_pre_fast_kernel", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
+            "frac": achieved / peak64 if peak64 else None, "traffic": ncu_traffic_bytes() if args.config == 2 and not args.small else None,
+            "peak_source": "measured in this job: dependent-free DFMA microbenchmark (rtrb_measure_fma_peak)",
+            "peak_fp32": peak32, "algorithmic_flops_per_launch": flops_frame, "kernel_ms": trace_ms,
+            "hbm": {"algorithmic_bytes_per_launch": frame_bytes, "peak_gbs": measured_hbm_gbs(),
+                    "achieved_gbs": frame_bytes / (trace_ms * 1e-3) / 1e9},
+            "note": "FP-issue bound path (SURVEY.md 8d): HBM traffic is the framebuffer write only; rank 0's kernel and counters",
+        }
         if world_size == 1:
-            flops_frame = flops_batch / B
-            achieved = flops_frame / (trace_ms * 1e-3) / 1e12
-            line["roofline"] = {
-                "bound": "fp64", "kernel": "trace_pre_fast_kernel", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
-                "frac": achieved / peak64 if peak64 else None, "traffic": ncu_traffic_bytes(),
-                "peak_source": "measured in this job: dependent-free DFMA microbenchmark (rtrb_measure_fma_peak)",
-                "peak_fp32": peak32, "algorithmic_flops_per_launch": flops_frame, "kernel_ms": trace_ms,
-                "hbm": {"algorithmic_bytes_per_launch": frame_bytes, "peak_gbs": measured_hbm_gbs(),
-                        "achieved_gbs": frame_bytes / (trace_ms * 1e-3) / 1e9},
-                "note": "FP-issue bound path (SURVEY.md 8d): HBM traffic is the 4 B/pixel framebuffer write only",
-            }
             line["cpu_baseline"] = cpu_baseline(args, world, cams[0], name)
         print(json.dumps(line))
     if dist is not None:
@@ -398,6 +426,15 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--precision", default="fast64", choices=["fast64", "strict"])
     ap.add_argument("--small", action="store_true", help="480x270 variant for quick checks (not a bench value)")
+    ap.add_argument("--pixel-format", default="rgb8", choices=["rgb8", "rgba8"],
+                    help="8-bit frame layout delivered (rgb8: alpha is the constant 255 and stays off the wire)")
+    ap.add_argument("--gather", default="store", choices=["store", "copy"],
+                    help="N > 1: how finished frames reach rank 0's slots (peer stores from the kernel / copy engine)")
+    ap.add_argument("--tile-split", action="store_true",
+                    help="N > 1: cut every frame into super-tiles across the ranks (strong scaling of heavy frames)")
+    ap.add_argument("--spp", type=int, default=0, help="override pre = max sample count (heavy configs at reduced cost)")
+    ap.add_argument("--count-one", action="store_true", help="count rays/FLOPs on one frame of the batch only")
+    ap.add_argument("--count-fast", action="store_true", help="take the counters from the FAST64 kernel (heavy configs)")
     ap.add_argument("--cpu-fraction", type=float, default=1.0, help="fraction of the frame width the CPU legs render")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

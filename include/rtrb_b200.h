@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RTRB_ABI_VERSION 1
+#define RTRB_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -50,12 +50,19 @@ enum {
 };
 
 /* ---- object kinds (world.yml `type:`; world.rb:28-34) -------------------------------------- */
-enum { RTRB_OBJ_PLANE = 0, RTRB_OBJ_SPHERE = 1 };
+enum { RTRB_OBJ_PLANE = 0, RTRB_OBJ_SPHERE = 1, RTRB_OBJ_BOX = 2 };
 
 /* ---- RNG modes ----------------------------------------------------------------------------- */
 enum {
   RTRB_RNG_CTR = 0,  /* Philox4x32-10 keyed by (seed; pixel, sample, ray path, purpose); device + oracle */
   RTRB_RNG_MT = 1    /* MT19937 genrand_res53 in the reference's consumption order; oracle only */
+};
+
+/* ---- rtrb_render_opts.pixel_format: layout of the 8-bit frame -------------------------------- */
+enum {
+  RTRB_FMT_RGBA8 = 0, /* H*W*4 bytes, alpha = 255: what array_to_color builds (camera.rb:153-156) */
+  RTRB_FMT_RGB8 = 1   /* H*W*3 bytes: alpha is the constant 255, so it need not cross PCIe; the caller
+                         (Camera#render_cuda) re-inserts it when it fills the PNG canvas */
 };
 
 /* ---- rtrb_render_opts.skip_outputs ----------------------------------------------------------- */
@@ -68,17 +75,17 @@ enum {
   RTRB_PREC_DEFAULT = 1
 };
 
-/* One entry of world.yml `world_objects` (plane.rb:9-15, sphere.rb:8-14), order preserved:
+/* One entry of world.yml `world_objects` (plane.rb:9-15, sphere.rb:8-14, box.rb:10-14), order preserved:
  * World#intersect's strict `<` (world.rb:48) makes the lowest index win distance ties. */
 typedef struct rtrb_object_desc {
   int32_t type;            /* RTRB_OBJ_* */
   int32_t texture;         /* index into rtrb_scene_desc.textures, -1 = untextured */
-  int32_t has_refraction;  /* plane: refractive_rate key present (plane.rb:57); sphere: must be 1 */
+  int32_t has_refraction;  /* plane / box: refractive_rate key present (plane.rb:57); sphere: must be 1 */
   int32_t reserved0;
-  double point[3];         /* sphere: center ; plane: point */
+  double point[3];         /* sphere: center ; plane: point ; box: point (its centre) */
   double radius;           /* sphere only */
-  double front[3];         /* plane normal, NOT normalised by the reference */
-  double up[3];            /* plane `up` */
+  double front[3];         /* plane normal / box front axis, NOT normalised by the reference */
+  double up[3];            /* plane / box `up` */
   double u_unit, v_unit;   /* plane uv units (plane.rb:81-85) */
   double greenwich_vec[3]; /* sphere texture frame (sphere.rb:111-120) */
   double north_pole_vec[3];
@@ -89,6 +96,10 @@ typedef struct rtrb_object_desc {
   double reflective_attenuation[3];
   double refractive_attenuation[3];
   double ambient[3];
+  /* box only (box.rb:10,22-58): extents along front / up / normalize(front x up).  The six bounded
+   * faces are derived by the library exactly as Box#initialize does.  A box ignores `texture`
+   * (Box never overrides local_lighting, world_object.rb:51-74 runs without a colour filter). */
+  double width_front, width_up, width_left;
 } rtrb_object_desc;
 
 /* One entry of world.yml `lights` (lights/light.rb:3-4, spot_light.rb:5). */
@@ -141,8 +152,10 @@ typedef struct rtrb_render_opts {
   int32_t skip_outputs; /* rtrb_render_device only: RTRB_SKIP_RGB | RTRB_SKIP_HIT drop the optional float RGB
                            (24 B/pixel) / hit-id (4 B/pixel) frames; 0 keeps both for rtrb_download */
   void* stream;         /* cudaStream_t to launch on; NULL = the renderer's own stream */
-  void* rgba_device_out;/* device pointer (possibly a peer mapping) the RGBA8 frame is written to;
+  void* rgba_device_out;/* device pointer (possibly a peer mapping) the 8-bit frame is written to;
                            NULL = the renderer's own framebuffer */
+  int32_t pixel_format; /* RTRB_FMT_*: layout of the 8-bit frame (device buffer and host copies alike) */
+  int32_t reserved0;
 } rtrb_render_opts;
 
 typedef struct rtrb_stats {
@@ -162,7 +175,8 @@ typedef struct rtrb_stats {
   uint64_t cover_plane, cover_plane_accepts;  /* WorldObject#cover_area on planes */
   uint64_t adaptive_pixels;   /* pixels taking the extra-sample branch (camera.rb:87-93) */
   uint64_t exact_tests;       /* FAST64 only: objects re-evaluated in strict FP64 after the FP32 cull */
-  uint64_t reserved[4];
+  uint64_t box_tests, box_accepts;            /* Box#intersect from World#intersect (box.rb:78-97) */
+  uint64_t cover_box, cover_box_accepts;      /* WorldObject#cover_area on boxes */
   uint32_t status;            /* RTRB_ST_* bits */
   int32_t first_bad_x, first_bad_y; /* lowest (y*W+x) pixel that set a status bit, -1 if none */
   uint32_t max_stack;         /* deepest work stack seen */
@@ -188,7 +202,8 @@ int rtrb_renderer_destroy(rtrb_renderer* r);
 int rtrb_render_device(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts,
                        rtrb_stats* stats_out);
 
-/* Copies the last frame to HOST buffers. rgba: H*W*4 bytes, row = y, column = x (camera.rb:98,105);
+/* Copies the last frame to HOST buffers. rgba: H*W*4 bytes (H*W*3 when the frame was rendered with
+ * RTRB_FMT_RGB8), row = y, column = x (camera.rb:98,105);
  * rgb_or_null: H*W*3 doubles = render_at's unclamped `color`; hit_or_null: H*W int32 primary hit
  * ids (index in world_objects, -1 miss, -2 highlight-terminated, -3 pixel not rendered). */
 int rtrb_download(rtrb_renderer* r, uint8_t* rgba, double* rgb_or_null, int32_t* hit_or_null);
@@ -201,7 +216,7 @@ int rtrb_render(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
  * device->host copy into rgba_host (pinned memory recommended) on a separate copy stream, then
  * returns; rtrb_wait blocks until that frame's bytes and stats are in host memory.  Up to four frames
  * may be in flight per renderer (tickets are consecutive integers; wait for them in order), so
- * later frames render while earlier ones cross PCIe.  RGBA8 only. */
+ * later frames render while earlier ones cross PCIe.  8-bit frame only (opts->pixel_format). */
 int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts, uint8_t* rgba_host,
                 int* ticket_out);
 int rtrb_wait(rtrb_renderer* r, int ticket, rtrb_stats* stats_out);
@@ -223,6 +238,15 @@ int rtrb_ipc_close(int device, void* ptr);
 int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_desc* cam,
                       const rtrb_render_opts* opts, uint8_t* rgba, double* rgb_or_null,
                       int32_t* hit_or_null, rtrb_stats* stats_out);
+
+/* Copy-engine form of the gather (whole frames dealt to ranks): queues a
+ * device-to-device copy of `bytes` from `src` (a buffer of this renderer's device) to `dst_peer` (a
+ * peer mapping, e.g. a frame slot of rank 0's framebuffer) on the renderer's copy stream, ordered
+ * after everything queued so far on `after_stream` (NULL = the renderer's own stream).  The render
+ * stream does not wait: the next frame renders while this one crosses NVLink. */
+int rtrb_peer_push(rtrb_renderer* r, const void* src, void* dst_peer, size_t bytes, void* after_stream);
+/* Makes `stream` (NULL = the renderer's own) wait for every rtrb_peer_push queued so far. */
+int rtrb_peer_push_join(rtrb_renderer* r, void* stream);
 
 /* Pure host helper (no GPU): the 32x32-pixel super-tiles of a width x height frame (optionally
  * clipped to window {x0,y0,x1,y1}, NULL = whole frame) that tile_rank renders out of tile_world,

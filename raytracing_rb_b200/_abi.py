@@ -2,7 +2,7 @@
 for field; tests/test_abi.py checks sizeof() against the values the compiled library reports."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 RTRB_OK, RTRB_ERR_INVALID, RTRB_ERR_CUDA, RTRB_ERR_RAISED, RTRB_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 
@@ -12,7 +12,8 @@ ST_MATH_DOMAIN = 1 << 2
 ST_STACK_OVERFLOW = 1 << 3
 ST_NAN_TO_INT = 1 << 4
 
-OBJ_PLANE, OBJ_SPHERE = 0, 1
+OBJ_PLANE, OBJ_SPHERE, OBJ_BOX = 0, 1, 2
+FMT_RGBA8, FMT_RGB8 = 0, 1
 RNG_CTR, RNG_MT = 0, 1
 PREC_STRICT, PREC_FAST64 = 0, 1
 PREC_DEFAULT = PREC_FAST64
@@ -32,6 +33,7 @@ class ObjectDesc(C.Structure):
         ("texture_u_offset", C.c_double), ("texture_v_offset", C.c_double),
         ("refractive_rate", C.c_double),
         ("diffuse_rate", D3), ("reflective_attenuation", D3), ("refractive_attenuation", D3), ("ambient", D3),
+        ("width_front", C.c_double), ("width_up", C.c_double), ("width_left", C.c_double),
     ]
 
 
@@ -73,6 +75,7 @@ class RenderOpts(C.Structure):
         ("tile_rank", C.c_int32), ("tile_world", C.c_int32),
         ("count_detail", C.c_int32), ("skip_outputs", C.c_int32),
         ("stream", C.c_void_p), ("rgba_device_out", C.c_void_p),
+        ("pixel_format", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -87,7 +90,8 @@ class Stats(C.Structure):
         ("cover_sphere", C.c_uint64), ("cover_sphere_full", C.c_uint64), ("cover_sphere_penumbra", C.c_uint64),
         ("cover_plane", C.c_uint64), ("cover_plane_accepts", C.c_uint64),
         ("adaptive_pixels", C.c_uint64), ("exact_tests", C.c_uint64),
-        ("reserved", C.c_uint64 * 4),
+        ("box_tests", C.c_uint64), ("box_accepts", C.c_uint64),
+        ("cover_box", C.c_uint64), ("cover_box_accepts", C.c_uint64),
         ("status", C.c_uint32), ("first_bad_x", C.c_int32), ("first_bad_y", C.c_int32),
         ("max_stack", C.c_uint32), ("device_ms", C.c_float), ("trace_ms", C.c_float),
     ]
@@ -96,7 +100,7 @@ class Stats(C.Structure):
         "samples", "rays", "shadow_queries", "highlight_hits", "hits", "local_shaded", "lit_lights", "mc_rays",
         "refractions", "texel_fetches", "sphere_tests", "sphere_accepts", "plane_tests", "plane_accepts",
         "cover_sphere", "cover_sphere_full", "cover_sphere_penumbra", "cover_plane", "cover_plane_accepts",
-        "adaptive_pixels",
+        "adaptive_pixels", "box_tests", "box_accepts", "cover_box", "cover_box_accepts",
     )
 
     def as_dict(self):

@@ -13,6 +13,7 @@ EXPORTS = (
     "rtrb_renderer_create", "rtrb_renderer_destroy",
     "rtrb_render_device", "rtrb_download", "rtrb_render", "rtrb_submit", "rtrb_wait",
     "rtrb_framebuffer_device_ptr", "rtrb_framebuffer_download", "rtrb_framebuffer_ipc_export", "rtrb_ipc_open", "rtrb_ipc_close",
+    "rtrb_peer_push", "rtrb_peer_push_join",
     "rtrb_render_multi", "rtrb_tile_partition", "rtrb_measure_fma_peak", "rtrb_launch_count",
 )
 
@@ -51,6 +52,8 @@ def lib():
     L.rtrb_framebuffer_ipc_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.rtrb_ipc_open.argtypes = [C.c_int, C.c_void_p, P(C.c_void_p)]
     L.rtrb_ipc_close.argtypes = [C.c_int, C.c_void_p]
+    L.rtrb_peer_push.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.rtrb_peer_push_join.argtypes = [C.c_void_p, C.c_void_p]
     L.rtrb_render_multi.argtypes = [P(C.c_void_p), C.c_int, P(_abi.CameraDesc), P(_abi.RenderOpts), C.c_void_p,
                                     C.c_void_p, C.c_void_p, P(_abi.Stats)]
     L.rtrb_tile_partition.argtypes = [C.c_int, C.c_int, P(C.c_int32), C.c_int, C.c_int, P(C.c_int32), C.c_int, P(C.c_int)]

@@ -128,6 +128,7 @@ struct FrameCtl {
 struct rtrb_renderer {
   int device = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t push_ev = nullptr, push_done_ev = nullptr;  // rtrb_peer_push ordering (no timing)
   FrameCtl main_ctl;       // synchronous calls
   FrameCtl pipe_ctl[RTRB_PIPE_SLOTS];  // rtrb_submit / rtrb_wait frame slots
   bool pipe_ready = false;
@@ -162,6 +163,7 @@ struct rtrb_renderer {
   // last frame
   int last_w = 0, last_h = 0;
   bool last_has_rgb = false, last_has_hit = false;
+  int last_bpp = 4;
   cudaStream_t last_stream = nullptr;
   bool timing_valid = false;
 };
@@ -522,6 +524,8 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     return fail(RTRB_ERR_UNSUPPORTED, "rng_mode %d: only the counter RNG runs on the device (MT19937 is oracle-only)", opts.rng_mode);
   if (opts.precision != RTRB_PREC_STRICT && opts.precision != RTRB_PREC_FAST64)
     return fail(RTRB_ERR_INVALID, "unknown precision mode %d", opts.precision);
+  if (opts.pixel_format != RTRB_FMT_RGBA8 && opts.pixel_format != RTRB_FMT_RGB8)
+    return fail(RTRB_ERR_INVALID, "unknown pixel format %d", opts.pixel_format);
   const int W = cam->width, H = cam->height;
   int x0 = opts.x0, y0 = opts.y0, x1 = opts.x1, y1 = opts.y1;
   if (x0 == 0 && y0 == 0 && x1 == 0 && y1 == 0) { x1 = W; y1 = H; }
@@ -625,6 +629,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.extra_count = reinterpret_cast<uint32_t*>(fc.d.p + RTRB_CNT_N + 4);
   P.extra_list = r->extra_list.p; P.extra_samples = r->extra_samples.p;
   P.count_detail = opts.count_detail;
+  P.pixel_format = opts.pixel_format;
   // a single sample with a positive threshold can never take the adaptive branch (variance == 0)
   P.fuse_resolve = (S == 1 && cam->variant_threshold > 0) ? 1 : 0;
 
@@ -662,6 +667,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   r->last_has_rgb = tg.rgb == r->rgb.p && tg.rgb != nullptr;
   r->last_has_hit = tg.hit == r->hit.p && tg.hit != nullptr;
   r->last_stream = stream;
+  r->last_bpp = opts.pixel_format == RTRB_FMT_RGB8 ? 3 : 4;
 
   // facts needed to finish the stats once the control block has been copied back
   fc.W = W; fc.H = H; fc.S = S; fc.E = E; fc.n_tiles = n_tiles; fc.detail = opts.count_detail != 0;
@@ -759,6 +765,8 @@ int rtrb_renderer_create(const rtrb_scene_desc* scene, int device, rtrb_renderer
   cudaError_t ce;
   if ((ce = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (ce = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (ce = cudaEventCreateWithFlags(&r->push_ev, cudaEventDisableTiming)) != cudaSuccess ||
+      (ce = cudaEventCreateWithFlags(&r->push_done_ev, cudaEventDisableTiming)) != cudaSuccess ||
       (ce = (cudaError_t)r->main_ctl.init()) != cudaSuccess) {
     rtrb_renderer_destroy(r);
     return fail(RTRB_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(ce));
@@ -780,6 +788,8 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   r->main_ctl.destroy();
   for (int i = 0; i < RTRB_PIPE_SLOTS; ++i) r->pipe_ctl[i].destroy();
   for (uint8_t* t : r->textures) cudaFree(t);
+  if (r->push_ev) cudaEventDestroy(r->push_ev);
+  if (r->push_done_ev) cudaEventDestroy(r->push_done_ev);
   if (r->stream) cudaStreamDestroy(r->stream);
   if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
   delete r;
@@ -797,7 +807,7 @@ int rtrb_download(rtrb_renderer* r, uint8_t* rgba, double* rgb_or_null, int32_t*
   CUDA_TRY(cudaSetDevice(r->device));
   cudaStream_t s = r->last_stream ? r->last_stream : r->stream;
   size_t px = (size_t)r->last_w * r->last_h;
-  if (rgba) CUDA_TRY(cudaMemcpyAsync(rgba, r->rgba.p, px * 4, cudaMemcpyDeviceToHost, s));
+  if (rgba) CUDA_TRY(cudaMemcpyAsync(rgba, r->rgba.p, px * (size_t)r->last_bpp, cudaMemcpyDeviceToHost, s));
   if (rgb_or_null) {
     if (!r->last_has_rgb) return fail(RTRB_ERR_INVALID, "the last frame kept no float RGB");
     CUDA_TRY(cudaMemcpyAsync(rgb_or_null, r->rgb.p, px * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -840,10 +850,12 @@ int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   const unsigned ticket = r->next_ticket;
   FrameCtl& fc = r->pipe_ctl[ticket % RTRB_PIPE_SLOTS];
   if (fc.in_flight) return fail(RTRB_ERR_INVALID, "%d frames are already in flight: call rtrb_wait first", RTRB_PIPE_SLOTS);
-  const size_t bytes = (size_t)cam->width * cam->height * 4;
-  if (cam->width > 0 && cam->height > 0 && fc.rgba.n < bytes) {
-    CUDA_TRY(fc.rgba.ensure(bytes));
-    CUDA_TRY(cudaMemsetAsync(fc.rgba.p, 0, bytes, r->stream));
+  const size_t bpp = (opts && opts->pixel_format == RTRB_FMT_RGB8) ? 3 : 4;
+  const size_t bytes = (size_t)cam->width * cam->height * bpp;
+  const size_t slot_bytes = (size_t)cam->width * cam->height * 4;
+  if (cam->width > 0 && cam->height > 0 && fc.rgba.n < slot_bytes) {
+    CUDA_TRY(fc.rgba.ensure(slot_bytes));
+    CUDA_TRY(cudaMemsetAsync(fc.rgba.p, 0, slot_bytes, r->stream));
   }
   rtrb_render_opts o;
   memset(&o, 0, sizeof(o));
@@ -923,6 +935,25 @@ int rtrb_ipc_close(int device, void* ptr) {
   return RTRB_OK;
 }
 
+int rtrb_peer_push(rtrb_renderer* r, const void* src, void* dst_peer, size_t bytes, void* after_stream) {
+  if (!r || !src || !dst_peer) return fail(RTRB_ERR_INVALID, "bad argument");
+  if (bytes == 0) return RTRB_OK;
+  CUDA_TRY(cudaSetDevice(r->device));
+  cudaStream_t after = after_stream ? (cudaStream_t)after_stream : r->stream;
+  CUDA_TRY(cudaEventRecord(r->push_ev, after));
+  CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, r->push_ev, 0));
+  CUDA_TRY(cudaMemcpyAsync(dst_peer, src, bytes, cudaMemcpyDefault, r->copy_stream));  // copy engine over NVLink
+  return RTRB_OK;
+}
+
+int rtrb_peer_push_join(rtrb_renderer* r, void* stream) {
+  if (!r) return fail(RTRB_ERR_INVALID, "renderer is NULL");
+  CUDA_TRY(cudaSetDevice(r->device));
+  CUDA_TRY(cudaEventRecord(r->push_done_ev, r->copy_stream));
+  CUDA_TRY(cudaStreamWaitEvent(stream ? (cudaStream_t)stream : r->stream, r->push_done_ev, 0));
+  return RTRB_OK;
+}
+
 int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_desc* cam,
                       const rtrb_render_opts* opts_in, uint8_t* rgba, double* rgb_or_null, int32_t* hit_or_null,
                       rtrb_stats* stats_out) {
@@ -990,7 +1021,7 @@ int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_
     uint64_t* a = &agg.samples;
     for (int i = 0; i < n; ++i) {
       const uint64_t* b = &st[i].samples;
-      for (int k = 0; k < 21; ++k) a[k] += b[k];
+      for (int k = 0; k < 25; ++k) a[k] += b[k];  // samples .. cover_box_accepts
       agg.status |= st[i].status;
       agg.max_stack = std::max(agg.max_stack, st[i].max_stack);
       agg.device_ms = std::max(agg.device_ms, st[i].device_ms);
@@ -1005,6 +1036,7 @@ int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_
   root->last_w = cam->width; root->last_h = cam->height;
   root->last_has_rgb = want_rgb; root->last_has_hit = want_hit;
   root->last_stream = root->stream;
+  root->last_bpp = base.pixel_format == RTRB_FMT_RGB8 ? 3 : 4;
   std::string keep = g_last_error;
   rc = rtrb_download(root, rgba, rgb_or_null, hit_or_null);
   if (rc) return rc;

@@ -469,6 +469,13 @@ __device__ __forceinline__ uint8_t quantise_u8(double c) {
 __device__ __forceinline__ void write_pixel(const FrameParams& P, int x, int y, double r, double g, double b) {
   size_t px = (size_t)y * P.width + x;
   if (P.rgb) { P.rgb[px * 3 + 0] = r; P.rgb[px * 3 + 1] = g; P.rgb[px * 3 + 2] = b; }
+  if (P.pixel_format == RTRB_FMT_RGB8) {
+    // alpha is the constant 255 (camera.rb:155): three byte stores; a warp's 8x4 pixel block is four
+    // 24-byte runs which the L2 merges before the frame leaves over PCIe / NVLink
+    uint8_t* o = P.rgba + px * 3;
+    o[0] = quantise_u8(r); o[1] = quantise_u8(g); o[2] = quantise_u8(b);
+    return;
+  }
   uchar4 q = make_uchar4(quantise_u8(r), quantise_u8(g), quantise_u8(b), 255);
   reinterpret_cast<uchar4*>(P.rgba)[px] = q;
 }

@@ -120,6 +120,8 @@ struct FrameParams {
   unsigned long long* work_counter;  // [2] persistent-kernel work claim counters (pre pass, extra pass)
   int32_t count_detail;
   int32_t fuse_resolve;        // pre == max == 1 style frames: the trace kernel writes the pixel itself
+  int32_t pixel_format;        // RTRB_FMT_*: 4 (RGBA8) or 3 (RGB8) bytes per pixel in `rgba`
+  int32_t pad_fmt;
 };
 
 enum {

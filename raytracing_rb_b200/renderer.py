@@ -25,7 +25,7 @@ class Frame:
 
 
 def make_opts(rng_mode=_abi.RNG_CTR, precision=_abi.PREC_DEFAULT, seed=1, window=None, tile_rank=0, tile_world=1,
-              count_detail=False, stream=None, rgba_device_out=None, skip_outputs=0):
+              count_detail=False, stream=None, rgba_device_out=None, skip_outputs=0, pixel_format=_abi.FMT_RGBA8):
     o = _abi.RenderOpts()
     o.rng_mode, o.precision, o.seed = rng_mode, precision, seed
     if window:
@@ -35,6 +35,7 @@ def make_opts(rng_mode=_abi.RNG_CTR, precision=_abi.PREC_DEFAULT, seed=1, window
     o.skip_outputs = skip_outputs
     o.stream = stream
     o.rgba_device_out = rgba_device_out
+    o.pixel_format = pixel_format
     return o
 
 
@@ -68,8 +69,8 @@ class Renderer:
         check(code, allow_raised=True)
         return (st.as_dict() if want_stats else None), code
 
-    def download(self, width, height, want_rgb=True, want_hit=True):
-        rgba = np.empty((height, width, 4), np.uint8)
+    def download(self, width, height, want_rgb=True, want_hit=True, channels=4):
+        rgba = np.empty((height, width, channels), np.uint8)
         rgb = np.empty((height, width, 3), np.float64) if want_rgb else None
         hit = np.empty((height, width), np.int32) if want_hit else None
         check(lib().rtrb_download(self._h, rgba.ctypes.data, rgb.ctypes.data if want_rgb else None,
@@ -80,7 +81,8 @@ class Renderer:
         """The frame-level call the Ruby shim binds (host buffers in, host buffers out)."""
         opts = opts or make_opts()
         H, W = cam.height, cam.width
-        rgba = out_rgba if out_rgba is not None else np.empty((H, W, 4), np.uint8)
+        channels = 3 if opts.pixel_format == _abi.FMT_RGB8 else 4
+        rgba = out_rgba if out_rgba is not None else np.empty((H, W, channels), np.uint8)
         rgb = np.empty((H, W, 3), np.float64) if want_rgb else None
         hit = np.empty((H, W), np.int32) if want_hit else None
         st = _abi.Stats()
@@ -103,6 +105,14 @@ class Renderer:
         code = lib().rtrb_wait(self._h, ticket, C.byref(st))
         check(code, allow_raised=True)
         return st.as_dict(), code
+
+    def peer_push(self, src_ptr, dst_peer_ptr, nbytes, after_stream=None):
+        """Copy-engine gather: queue a D2D copy to a peer mapping behind `after_stream` (see rtrb_peer_push)."""
+        check(lib().rtrb_peer_push(self._h, C.c_void_p(src_ptr), C.c_void_p(dst_peer_ptr), nbytes,
+                                   C.c_void_p(after_stream) if after_stream else None))
+
+    def peer_push_join(self, stream=None):
+        check(lib().rtrb_peer_push_join(self._h, C.c_void_p(stream) if stream else None))
 
     def framebuffer_ptr(self, width, height):
         p = C.c_void_p()
