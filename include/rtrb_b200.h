@@ -180,8 +180,8 @@ typedef struct rtrb_stats {
   uint32_t status;            /* RTRB_ST_* bits */
   int32_t first_bad_x, first_bad_y; /* lowest (y*W+x) pixel that set a status bit, -1 if none */
   uint32_t max_stack;         /* deepest work stack seen */
-  float device_ms;            /* CUDA-event time of the frame's kernels on the launch stream */
-  float trace_ms;             /* CUDA-event time of the dominant kernel alone (trace over the pre samples) */
+  float device_ms;            /* CUDA-event time of the frame's kernels on the launch stream (0 for rtrb_submit frames) */
+  float trace_ms;             /* CUDA-event time of the dominant kernel alone (trace over the pre samples); 0 likewise */
 } rtrb_stats;
 
 typedef struct rtrb_renderer rtrb_renderer; /* opaque: scene SoA + scratch + framebuffers on ONE device */

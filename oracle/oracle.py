@@ -39,6 +39,7 @@ def lib():
         L.rtrb_oracle_object_distance.restype = C.c_double
         L.rtrb_oracle_object_distance.argtypes = [P(_abi.CameraDesc)]
         L.rtrb_oracle_intersect.argtypes = [C.c_void_p, C.c_int, P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_int)]
+        L.rtrb_oracle_box_face.argtypes = [C.c_void_p, C.c_int, P(C.c_double), P(C.c_double)]
         L.rtrb_oracle_world_intersect.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_double)]
         L.rtrb_oracle_cover_area.restype = C.c_double
         L.rtrb_oracle_cover_area.argtypes = [C.c_void_p, C.c_int, P(C.c_double), C.c_double, P(C.c_double)]
@@ -94,6 +95,9 @@ class OracleScene:
         if not ok:
             return None
         return list(out[:3]), ("in" if din.value else "out"), list(out[3:])
+
+    def box_face(self, obj, o, d):
+        return lib().rtrb_oracle_box_face(self._h, obj, _d3(o), _d3(d))
 
     def world_intersect(self, o, d):
         out = (C.c_double * 3)()

@@ -191,6 +191,7 @@ struct Hit {  // what obj.intersect returns: [intersection, direction, delta]
   V3 intersection;
   bool dir_in = false;  // :in / :out
   V3 delta;
+  int data_index = -1;  // Box#intersect's `data = { index: index }` (box.rb:89): the face that was hit
 };
 
 struct Params {  // intersect_parameters result
@@ -206,7 +207,8 @@ struct Counters {
   uint64_t samples = 0, rays = 0, shadow_queries = 0, highlight_hits = 0, hits = 0, local_shaded = 0,
            lit_lights = 0, mc_rays = 0, refractions = 0, texel_fetches = 0, sphere_tests = 0,
            sphere_accepts = 0, plane_tests = 0, plane_accepts = 0, cover_sphere = 0, cover_sphere_full = 0,
-           cover_sphere_penumbra = 0, cover_plane = 0, cover_plane_accepts = 0, adaptive_pixels = 0;
+           cover_sphere_penumbra = 0, cover_plane = 0, cover_plane_accepts = 0, adaptive_pixels = 0,
+           box_tests = 0, box_accepts = 0, cover_box = 0, cover_box_accepts = 0;
   uint32_t max_stack = 0;
   void add(const Counters& o) {
     samples += o.samples; rays += o.rays; shadow_queries += o.shadow_queries; highlight_hits += o.highlight_hits;
@@ -216,6 +218,7 @@ struct Counters {
     cover_sphere += o.cover_sphere; cover_sphere_full += o.cover_sphere_full;
     cover_sphere_penumbra += o.cover_sphere_penumbra; cover_plane += o.cover_plane;
     cover_plane_accepts += o.cover_plane_accepts; adaptive_pixels += o.adaptive_pixels;
+    box_tests += o.box_tests; box_accepts += o.box_accepts; cover_box += o.cover_box; cover_box_accepts += o.cover_box_accepts;
     max_stack = std::max(max_stack, o.max_stack);
   }
 };
@@ -243,7 +246,8 @@ struct WorldObject {  // src/objects/world_object.rb
   Texture texture;
   virtual ~WorldObject() {}
   virtual Hit intersect(const Ray& ray) const = 0;
-  virtual Params intersect_parameters(const Ray& ray, const V3& intersection, bool dir_in, const V3& delta) const = 0;
+  virtual Params intersect_parameters(const Ray& ray, const V3& intersection, bool dir_in, const V3& delta,
+                                      int data_index = -1) const = 0;
   virtual double cover_area(const V3& light_position, double light_radius, const V3& target_position) const = 0;
   virtual V3 local_lighting(const V3& position, const std::vector<LitLight>& lights, const V3& normal_vector) const = 0;
 
@@ -330,7 +334,7 @@ struct Sphere : WorldObject {  // src/objects/sphere.rb
     return h;
   }
   // Sphere#intersect_parameters, :88-101
-  Params intersect_parameters(const Ray& ray, const V3& intersection, bool dir_in, const V3& delta) const override {
+  Params intersect_parameters(const Ray& ray, const V3& intersection, bool dir_in, const V3& delta, int = -1) const override {
     Params p;
     p.n = dir_in ? vsub(intersection, center) : vsub(center, intersection);
     p.reflection = reflection_by_ray_and_n(ray, p.n, intersection, delta);
@@ -412,7 +416,7 @@ struct Plane : WorldObject {  // src/objects/plane.rb
     return h;
   }
   // Plane#intersect_parameters, :54-67
-  Params intersect_parameters(const Ray& ray, const V3& intersection, bool, const V3& delta) const override {
+  Params intersect_parameters(const Ray& ray, const V3& intersection, bool, const V3& delta, int = -1) const override {
     Params p;
     p.n = vdot(front, ray.front) > 0 ? vneg(front) : front;
     p.reflection = reflection_by_ray_and_n(ray, p.n, intersection, delta);
@@ -442,6 +446,77 @@ struct Plane : WorldObject {  // src/objects/plane.rb
       return base_local_lighting(position, lights, normal_vector, &f);
     }
     return base_local_lighting(position, lights, normal_vector, &light_filter);
+  }
+};
+
+
+// src/objects/box.rb — six bounded faces built from Plane.create_from_scratch (plane.rb:17-19: no
+// attributes but the ones Box#initialize assigns), intersect = nearest face hit whose (u, v) lies in
+// [-0.5, 0.5]^2.  cover_area, local_lighting and path_tracing are WorldObject's (no override), so a
+// box casts hard shadows only and never samples its texture.
+struct Box : WorldObject {
+  V3 point, front, up;
+  double width_front = 0, width_up = 0, width_left = 0;
+  Plane planes[6];  // up, bottom, front, back, left, right (box.rb:60-65)
+
+  // Box#initialize, box.rb:15-74
+  void init() {
+    V3 left = vnormalize(vcross(front, up));  // :23
+    auto face = [&](int k, const V3& f, const V3& u, const V3& pt, double uu, double vu) {
+      Plane& p = planes[k];
+      p.front = f; p.up = u; p.point = pt; p.u_unit = uu; p.v_unit = vu;
+      p.reflective_attenuation = reflective_attenuation;  // :66-72
+      p.refractive_attenuation = refractive_attenuation;
+      p.refractive_rate = refractive_rate;
+      p.has_refraction = has_refraction;                  // `if self.refractive_rate` on the face (plane.rb:57)
+      p.diffuse_rate = diffuse_rate;
+      p.reinit();
+    };
+    face(0, up, left, vadd(point, vmul(vmul(up, width_up), 0.5)), width_front, width_left);            // :25-29
+    face(1, vneg(up), left, vsub(point, vmul(vmul(up, width_up), 0.5)), width_front, width_left);      // :30-34
+    face(2, front, up, vadd(point, vmul(vmul(front, width_front), 0.5)), width_left, width_up);        // :37-41
+    face(3, vneg(front), up, vsub(point, vmul(vmul(front, width_front), 0.5)), width_left, width_up);  // :42-46
+    V3 left2 = vnormalize(vcross(front, up));  // :49
+    face(4, left2, up, vadd(point, vmul(vmul(left2, width_left), 0.5)), width_front, width_up);        // :50-54
+    face(5, vneg(left2), up, vsub(point, vmul(vmul(left2, width_left), 0.5)), width_front, width_up);  // :55-59
+  }
+  // Box#intersect, box.rb:80-99
+  Hit intersect(const Ray& ray) const override {
+    const bool counting = g_ctx && g_ctx->counting_world_intersect;
+    if (counting) { g_ctx->cnt.box_tests++; g_ctx->counting_world_intersect = false; }  // faces are not world planes
+    double nearest_dis = INFINITY;
+    Hit nearest;
+    for (int index = 0; index < 6; ++index) {
+      const Plane& plane = planes[index];
+      Hit h = plane.intersect(ray);
+      if (h.ok) {
+        double u, v;
+        plane.get_uv(h.intersection, &u, &v);
+        if (-0.5 <= u && u <= 0.5 && -0.5 <= v && v <= 0.5) {
+          double d = vsub(h.intersection, ray.position).r;
+          if (d < nearest_dis) {
+            nearest_dis = d;
+            nearest = h;
+            nearest.data_index = index;
+          }
+        }
+      }
+    }
+    if (counting) { g_ctx->counting_world_intersect = true; if (nearest.ok) g_ctx->cnt.box_accepts++; }
+    return nearest;
+  }
+  // Box#intersect_parameters, box.rb:102-107
+  Params intersect_parameters(const Ray& ray, const V3& intersection, bool dir_in, const V3& delta, int data_index) const override {
+    return planes[data_index].intersect_parameters(ray, intersection, dir_in, delta);
+  }
+  double cover_area(const V3& light_position, double, const V3& target_position) const override {  // world_object.rb:41-49
+    if (g_ctx) g_ctx->cnt.cover_box++;
+    int f = base_cover_area(light_position, target_position);
+    if (f && g_ctx) g_ctx->cnt.cover_box_accepts++;
+    return f;
+  }
+  V3 local_lighting(const V3& position, const std::vector<LitLight>& lights, const V3& normal_vector) const override {
+    return base_local_lighting(position, lights, normal_vector, nullptr);  // world_object.rb:51-74, color_filter = nil
   }
 };
 
@@ -583,7 +658,7 @@ struct RayTracer {
     if (!object) { if (primary_hit) *primary_hit = -1; return; }
     if (primary_hit) *primary_hit = object->index;
     g_ctx->cnt.hits++;
-    Params p = object->intersect_parameters(it.ray, h.intersection, h.dir_in, h.delta);  // :80
+    Params p = object->intersect_parameters(it.ray, h.intersection, h.dir_in, h.delta, h.data_index);  // :80
     const uint32_t K = (uint32_t)(mc_times + 2);
     // reflection child, :87-103 (always exists)
     rays->push_back(RayItem{p.reflection, it.trace_depth - 1, vmul(it.attenuation, object->reflective_attenuation), it.path * K + 0u});
@@ -726,6 +801,11 @@ static OracleScene* build_scene(const rtrb_scene_desc* sd) {
         sp->ninety_degree_east_vec = vcross(sp->north_pole_vec, sp->greenwich_vec);  // sphere.rb:19
       }
       wo = std::move(sp);
+    } else if (o.type == RTRB_OBJ_BOX) {
+      auto bx = std::make_unique<Box>();
+      bx->point = v3(o.point); bx->front = v3(o.front); bx->up = v3(o.up);
+      bx->width_front = o.width_front; bx->width_up = o.width_up; bx->width_left = o.width_left;
+      wo = std::move(bx);
     } else {
       auto pl = std::make_unique<Plane>();
       pl->point = v3(o.point); pl->front = v3(o.front); pl->up = v3(o.up);
@@ -740,7 +820,8 @@ static OracleScene* build_scene(const rtrb_scene_desc* sd) {
     wo->reflective_attenuation = v3(o.reflective_attenuation);
     wo->refractive_attenuation = v3(o.refractive_attenuation);
     wo->ambient = v3(o.ambient);
-    if (o.texture >= 0) {
+    if (o.type == RTRB_OBJ_BOX) static_cast<Box*>(wo.get())->init();  // needs the material (box.rb:66-72)
+    if (o.texture >= 0 && o.type != RTRB_OBJ_BOX) {
       wo->has_texture = true;
       const rtrb_texture_desc& t = sd->textures[o.texture];
       wo->texture.width = t.width; wo->texture.height = t.height;
@@ -838,6 +919,8 @@ int rtrb_oracle_render(void* scene, const rtrb_camera_desc* cd, const rtrb_rende
     stats->cover_sphere_full = c.cover_sphere_full; stats->cover_sphere_penumbra = c.cover_sphere_penumbra;
     stats->cover_plane = c.cover_plane; stats->cover_plane_accepts = c.cover_plane_accepts;
     stats->adaptive_pixels = c.adaptive_pixels; stats->max_stack = c.max_stack;
+    stats->box_tests = c.box_tests; stats->box_accepts = c.box_accepts;
+    stats->cover_box = c.cover_box; stats->cover_box_accepts = c.cover_box_accepts;
     stats->status = status;
     stats->first_bad_x = first_bad < 0 ? -1 : (int32_t)(first_bad / H);
     stats->first_bad_y = first_bad < 0 ? -1 : (int32_t)(first_bad % H);
@@ -866,6 +949,16 @@ int rtrb_oracle_intersect(void* scene, int obj, const double* o, const double* d
   for (int i = 0; i < 3; ++i) { out6[i] = h.intersection.v[i]; out6[3 + i] = h.delta.v[i]; }
   *dir_in = h.dir_in;
   return 1;
+}
+// Box#intersect's data[:index] (box.rb:89) for object `obj`: the face hit (0 up, 1 bottom, 2 front, 3 back,
+// 4 left, 5 right), -1 on a miss or when the object is not a box
+int rtrb_oracle_box_face(void* scene, int obj, const double* o, const double* d) {
+  Ctx ctx; g_ctx = &ctx;
+  const OracleScene* s = (const OracleScene*)scene;
+  Ray ray{v3(d), v3(o)};
+  Hit h = s->world.world_objects[obj]->intersect(ray);
+  g_ctx = nullptr;
+  return h.ok ? h.data_index : -1;
 }
 // World#intersect: returns object index or -1; out = intersection(3)
 int rtrb_oracle_world_intersect(void* scene, const double* o, const double* d, double* out3) {
@@ -927,7 +1020,7 @@ int rtrb_oracle_intersect_parameters(void* scene, int obj, const double* o, cons
   const WorldObject* w = s->world.world_objects[obj].get();
   Hit h = w->intersect(ray);
   if (!h.ok) { g_ctx = nullptr; return -1; }
-  Params p = w->intersect_parameters(ray, h.intersection, h.dir_in, h.delta);
+  Params p = w->intersect_parameters(ray, h.intersection, h.dir_in, h.delta, h.data_index);
   g_ctx = nullptr;
   for (int i = 0; i < 3; ++i) {
     n3[i] = p.n.v[i];

@@ -9,7 +9,7 @@ from ._abi import PREC_DEFAULT, PREC_FAST64, PREC_STRICT, RNG_CTR, RNG_MT
 from .camera import Camera, write_png
 from .configurable_object import ConfigurableObject
 from .lights import Light, SpotLight
-from .objects import Plane, Sphere, WorldObject
+from .objects import Box, Plane, Sphere, WorldObject
 from .renderer import (Frame, Renderer, device_count, ipc_close, ipc_open, make_opts, measure_fma_peak,
                        render_multi, tile_partition)
 from .texture import Texture
@@ -17,7 +17,7 @@ from .vec3 import Vec3
 from .world import World
 
 __all__ = [
-    "Camera", "World", "Sphere", "Plane", "WorldObject", "Light", "SpotLight", "Texture", "Vec3",
+    "Camera", "World", "Sphere", "Plane", "Box", "WorldObject", "Light", "SpotLight", "Texture", "Vec3",
     "ConfigurableObject", "Renderer", "Frame", "make_opts", "render_multi", "measure_fma_peak",
     "device_count", "ipc_open", "ipc_close", "write_png", "tile_partition",
     "PREC_STRICT", "PREC_FAST64", "PREC_DEFAULT", "RNG_CTR", "RNG_MT",

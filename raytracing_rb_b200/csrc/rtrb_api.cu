@@ -101,17 +101,17 @@ struct DevBuf {
 struct FrameCtl {
   DevBuf<unsigned long long> d;
   unsigned long long* h = nullptr;  // pinned host mirror
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr, copied = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr, copied = nullptr, ctl_copied = nullptr;
   DevBuf<uint8_t> rgba;             // pipeline slots own a framebuffer; the main slot uses rtrb_renderer::rgba
   // facts of the frame in flight, needed to finish its stats later
   int W = 0, H = 0, S = 0, E = 0, n_tiles = 0;
-  bool detail = false, in_flight = false;
+  bool detail = false, in_flight = false, timed = false;
   size_t px_count = 0;
   int init() {
     cudaError_t e;
     if ((e = d.ensure(RTRB_FCB_WORDS)) != cudaSuccess) return (int)e;
     if ((e = cudaMallocHost((void**)&h, RTRB_FCB_WORDS * sizeof(unsigned long long))) != cudaSuccess) return (int)e;
-    cudaEvent_t* evs[5] = {&ev0, &ev1, &evt0, &evt1, &copied};
+    cudaEvent_t* evs[6] = {&ev0, &ev1, &evt0, &evt1, &copied, &ctl_copied};
     for (auto ev : evs)
       if ((e = cudaEventCreate(ev)) != cudaSuccess) return (int)e;
     return 0;
@@ -120,25 +120,26 @@ struct FrameCtl {
     d.release(); rgba.release();
     if (h) cudaFreeHost(h);
     h = nullptr;
-    cudaEvent_t* evs[5] = {&ev0, &ev1, &evt0, &evt1, &copied};
+    cudaEvent_t* evs[6] = {&ev0, &ev1, &evt0, &evt1, &copied, &ctl_copied};
     for (auto ev : evs) { if (*ev) cudaEventDestroy(*ev); *ev = nullptr; }
   }
 };
 
 struct rtrb_renderer {
   int device = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, ctl_stream = nullptr;
   cudaEvent_t push_ev = nullptr, push_done_ev = nullptr;  // rtrb_peer_push ordering (no timing)
   FrameCtl main_ctl;       // synchronous calls
   FrameCtl pipe_ctl[RTRB_PIPE_SLOTS];  // rtrb_submit / rtrb_wait frame slots
   bool pipe_ready = false;
   unsigned next_ticket = 0;
   // baked scene
-  int n_objects = 0, n_lights = 0;
+  int n_objects = 0, n_lights = 0, n_boxes = 0;
   double max_distance = 0, soft_shadow_exponent = 0;
   DevBuf<DevGeom> geom;
   DevBuf<DevMat> mat;
   DevBuf<DevLight> lights;
+  DevBuf<DevBox> boxes;
   // FP32 filter view (FAST64)
   DevBuf<float4> cull_sph, cull_pl;
   DevBuf<BvhNode> bvh;
@@ -152,6 +153,7 @@ struct rtrb_renderer {
   // per-frame scratch
   DevBuf<int32_t> tiles;
   std::vector<int32_t> tiles_host;     // global ids ty * stx_count + tx
+  size_t tiles_px_count = 0;           // pixels of the window covered by tiles_host
   DevBuf<double> lens_tab;             // [W + H] per-column / per-row retina offsets
   double lens_key[4] = {0, 0, 0, 0};   // (W, H, retina_width, retina_height) the table was built for
   int tiles_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
@@ -296,8 +298,13 @@ int validate_scene(const rtrb_scene_desc* s) {
   if (s->n_lights > 0 && !s->lights) return fail(RTRB_ERR_INVALID, "lights is NULL");
   for (int i = 0; i < s->n_objects; ++i) {
     const rtrb_object_desc& o = s->objects[i];
-    if (o.type != RTRB_OBJ_PLANE && o.type != RTRB_OBJ_SPHERE)
+    if (o.type != RTRB_OBJ_PLANE && o.type != RTRB_OBJ_SPHERE && o.type != RTRB_OBJ_BOX)
       return fail(RTRB_ERR_UNSUPPORTED, "object %d: unknown type %d", i, o.type);
+    if (o.type == RTRB_OBJ_BOX) {
+      H3 c = hcross(h3(o.front), h3(o.up));
+      if (hnorm(c) == 0)  // box.rb:23 `front.cross(up).normalize` raises 'zero vector' in World#initialize
+        return fail(RTRB_ERR_INVALID, "object %d: box front x up is the zero vector (fast_4d_matrix.c:290 would raise)", i);
+    }
     if (o.texture >= s->n_textures) return fail(RTRB_ERR_INVALID, "object %d: texture index out of range", i);
     if (o.type == RTRB_OBJ_SPHERE && !o.has_refraction)
       return fail(RTRB_ERR_INVALID, "object %d: a sphere needs refractive_rate (sphere.rb:93 divides unconditionally)", i);
@@ -323,6 +330,8 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
   }
   std::vector<DevGeom> geom(s->n_objects);
   std::vector<DevMat> mat(s->n_objects);
+  std::vector<DevBox> boxes;
+  std::vector<double> box_radius;  // filter bound per box (INFINITY = none)
   for (int i = 0; i < s->n_objects; ++i) {
     const rtrb_object_desc& o = s->objects[i];
     DevGeom& g = geom[i];
@@ -333,6 +342,43 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
     g.px = o.point[0]; g.py = o.point[1]; g.pz = o.point[2];
     g.radius = o.type == RTRB_OBJ_SPHERE ? o.radius : 0.0;
     g.nx = o.front[0]; g.ny = o.front[1]; g.nz = o.front[2];
+    if (o.type == RTRB_OBJ_BOX) {
+      // Box#initialize (box.rb:22-73) in the reference's evaluation order
+      const H3 pt = h3(o.point), fr = h3(o.front), up = h3(o.up);
+      const H3 left = hnormalize(hcross(fr, up));
+      const H3 nfr = H3{-fr.x, -fr.y, -fr.z}, nup = H3{-up.x, -up.y, -up.z}, nleft = H3{-left.x, -left.y, -left.z};
+      struct Spec { H3 front, up, point; double uu, vu; };
+      const Spec spec[6] = {
+          {up, left, hadd(pt, hmul(hmul(up, o.width_up), 0.5)), o.width_front, o.width_left},
+          {nup, left, hsub(pt, hmul(hmul(up, o.width_up), 0.5)), o.width_front, o.width_left},
+          {fr, up, hadd(pt, hmul(hmul(fr, o.width_front), 0.5)), o.width_left, o.width_up},
+          {nfr, up, hsub(pt, hmul(hmul(fr, o.width_front), 0.5)), o.width_left, o.width_up},
+          {left, up, hadd(pt, hmul(hmul(left, o.width_left), 0.5)), o.width_front, o.width_up},
+          {nleft, up, hsub(pt, hmul(hmul(left, o.width_left), 0.5)), o.width_front, o.width_up}};
+      DevBox bx;
+      double bound = 0;
+      // front _|_ up makes every face frame (left^, up^) orthonormal and in-plane, so a face's accepted
+      // region is the rectangle |u|,|v| <= 1/2 around its point; otherwise the filter gets no bound
+      const double fu = (fr.x * up.x + fr.y * up.y + fr.z * up.z) / (hnorm(fr) * hnorm(up));
+      bool bounded = fabs(fu) < 1e-9;
+      for (int k = 0; k < 6; ++k) {
+        DevBoxFace& F = bx.f[k];
+        const H3 fl = hnormalize(hcross(spec[k].front, spec[k].up));  // Plane#reinit, plane.rb:21-23
+        const H3 l2 = hnormalize(fl), u2 = hnormalize(spec[k].up);     // Plane#get_uv, plane.rb:82-83
+        F.px = spec[k].point.x; F.py = spec[k].point.y; F.pz = spec[k].point.z;
+        F.nx = spec[k].front.x; F.ny = spec[k].front.y; F.nz = spec[k].front.z;
+        F.lx = l2.x; F.ly = l2.y; F.lz = l2.z;
+        F.ux = u2.x; F.uy = u2.y; F.uz = u2.z;
+        F.u_unit = spec[k].uu; F.v_unit = spec[k].vu;
+        const double half = 0.5 * sqrt(spec[k].uu * spec[k].uu + spec[k].vu * spec[k].vu);
+        const double reach = hnorm(hsub(spec[k].point, pt)) + half;
+        if (!(reach == reach) || reach > 1e30) bounded = false;
+        bound = fmax(bound, reach);
+      }
+      box_radius.push_back(bounded ? bound * 1.001 : (double)INFINITY);
+      g.aux = (int32_t)boxes.size();
+      boxes.push_back(bx);
+    }
     for (int k = 0; k < 3; ++k) {
       m.diffuse[k] = o.diffuse_rate[k]; m.refl[k] = o.reflective_attenuation[k];
       m.refr[k] = o.refractive_attenuation[k]; m.ambient[k] = o.ambient[k];
@@ -347,7 +393,7 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
     m.u_unit = o.u_unit; m.v_unit = o.v_unit;
     m.hscale = o.texture_horizontal_scale; m.vscale = o.texture_vertical_scale;
     m.uoff = o.texture_u_offset; m.voff = o.texture_v_offset;
-    if (o.texture >= 0) {
+    if (o.texture >= 0 && o.type != RTRB_OBJ_BOX) {  // a box never samples its texture (box.rb has no local_lighting)
       m.tex = r->textures[o.texture];
       m.tex_w = s->textures[o.texture].width;
       m.tex_h = s->textures[o.texture].height;
@@ -381,11 +427,15 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
   float m_scene = 0.0f;
   for (int i = 0; i < s->n_objects; ++i) {
     const rtrb_object_desc& o = s->objects[i];
-    if (o.type == RTRB_OBJ_SPHERE) {
+    if (o.type == RTRB_OBJ_SPHERE || o.type == RTRB_OBJ_BOX) {
+      // a box enters the sphere filter through its bounding sphere (flagged: line test only)
+      const bool is_box = o.type == RTRB_OBJ_BOX;
+      const double rad = is_box ? box_radius[geom[i].aux] : o.radius;
       BvhBuildSphere bs;
-      bs.c[0] = o.point[0]; bs.c[1] = o.point[1]; bs.c[2] = o.point[2]; bs.r = o.radius; bs.world_index = i;
+      bs.c[0] = o.point[0]; bs.c[1] = o.point[1]; bs.c[2] = o.point[2]; bs.r = rad; bs.world_index = i;
+      bs.bound_only = is_box ? 1 : 0;
       bsph.push_back(bs);
-      double cm = fmax(fabs(o.point[0]), fmax(fabs(o.point[1]), fabs(o.point[2]))) + fabs(o.radius);
+      double cm = fmax(fabs(o.point[0]), fmax(fabs(o.point[1]), fabs(o.point[2]))) + (fabs(rad) < 1e30 ? fabs(rad) : 0.0);
       m_scene = fmaxf(m_scene, nextafterf((float)cm, INFINITY));
     } else {
       double n1 = fabs(o.front[0]) + fabs(o.front[1]) + fabs(o.front[2]);
@@ -399,7 +449,14 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
   std::vector<BvhNode> nodes;
   if ((int)bsph.size() > RTRB_BVH_MIN_SPHERES) nodes = rtrb_bvh::build_tree(bsph);
   for (const BvhBuildSphere& bs : bsph) {
-    csph.push_back(make_float4((float)bs.c[0], (float)bs.c[1], (float)bs.c[2], (float)bs.r));
+    float w = (float)bs.r;
+    if (bs.bound_only) {  // rounded up, sign bit set
+      w = fabsf(w);
+      if ((double)w < fabs(bs.r)) w = nextafterf(w, INFINITY);
+      w = -w;
+      if (w == 0.0f) w = -0.0f;
+    }
+    csph.push_back(make_float4((float)bs.c[0], (float)bs.c[1], (float)bs.c[2], w));
     isph.push_back(bs.world_index);
   }
   CUDA_TRY(r->bvh.ensure(std::max<size_t>(1, nodes.size())));
@@ -446,6 +503,9 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
   CUDA_TRY(r->geom.ensure(std::max(1, s->n_objects)));
   CUDA_TRY(r->mat.ensure(std::max(1, s->n_objects)));
   CUDA_TRY(r->lights.ensure(std::max(1, s->n_lights)));
+  CUDA_TRY(r->boxes.ensure(std::max<size_t>(1, boxes.size())));
+  r->n_boxes = (int)boxes.size();
+  if (!boxes.empty()) CUDA_TRY(cudaMemcpy(r->boxes.p, boxes.data(), boxes.size() * sizeof(DevBox), cudaMemcpyHostToDevice));
   if (s->n_objects) {
     CUDA_TRY(cudaMemcpy(r->geom.p, geom.data(), geom.size() * sizeof(DevGeom), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(r->mat.p, mat.data(), mat.size() * sizeof(DevMat), cudaMemcpyHostToDevice));
@@ -572,6 +632,13 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     }
     CUDA_TRY(cudaStreamSynchronize(stream));
     memcpy(r->tiles_key, key, sizeof(key));
+    r->tiles_px_count = 0;
+    for (int b : r->tiles_host) {
+      int tx = b % stx_count, ty = b / stx_count;
+      int ax0 = std::max(x0, tx * RTRB_SUPER), ax1 = std::min(x1, (tx + 1) * RTRB_SUPER);
+      int ay0 = std::max(y0, ty * RTRB_SUPER), ay1 = std::min(y1, (ty + 1) * RTRB_SUPER);
+      if (ax1 > ax0 && ay1 > ay0) r->tiles_px_count += (size_t)(ax1 - ax0) * (ay1 - ay0);
+    }
   }
   // ---- lens tables (cached): the per-column / per-row scalars of camera.rb:133-134, evaluated on the
   // host in the reference's order so the device does two loads instead of two FP64 divisions per sample
@@ -603,7 +670,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   bake_camera(P, cam);
   P.max_distance = r->max_distance; P.soft_shadow_exponent = r->soft_shadow_exponent;
   P.n_objects = r->n_objects; P.n_lights = r->n_lights;
-  P.geom = r->geom.p; P.mat = r->mat.p; P.lights = r->lights.p;
+  P.geom = r->geom.p; P.mat = r->mat.p; P.lights = r->lights.p; P.boxes = r->boxes.p;
   P.cull_sph = r->cull_sph.p; P.sph_index = r->sph_index.p; P.cull_pl = r->cull_pl.p; P.pl_index = r->pl_index.p;
   P.lights_f = r->lights_f.p; P.n_sph = r->n_sph; P.n_pl = r->n_pl; P.bvh = r->bvh.p;
   P.m_scene = r->m_scene; P.max_distance_f = r->max_distance_f;
@@ -628,14 +695,18 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.status = reinterpret_cast<uint32_t*>(fc.d.p + RTRB_CNT_N + 3);
   P.extra_count = reinterpret_cast<uint32_t*>(fc.d.p + RTRB_CNT_N + 4);
   P.extra_list = r->extra_list.p; P.extra_samples = r->extra_samples.p;
-  P.count_detail = opts.count_detail;
+  // the Box code lives only in the full-counter kernel variants (rtrb_trace.cuh, trace_dispatch)
+  P.count_detail = (opts.count_detail || r->n_boxes > 0) ? 1 : 0;
   P.pixel_format = opts.pixel_format;
   // a single sample with a positive threshold can never take the adaptive branch (variance == 0)
   P.fuse_resolve = (S == 1 && cam->variant_threshold > 0) ? 1 : 0;
 
   const bool strict = opts.precision == RTRB_PREC_STRICT;
-  // timing events only when somebody will read them (stats now, or at rtrb_wait)
-  const bool timed = stats_out != nullptr || ctl != nullptr;
+  // timing events only for the blocking calls that return stats: a timestamp between two kernels keeps
+  // frame i+1 from starting under frame i's tail, so pipelined frames (rtrb_submit) are not timed and
+  // report device_ms = trace_ms = 0
+  const bool timed = stats_out != nullptr;
+  fc.timed = timed;
   if (timed) CUDA_TRY(cudaEventRecord(fc.ev0, stream));
   CUDA_TRY(cudaMemsetAsync(fc.d.p, 0, RTRB_FCB_WORDS * sizeof(unsigned long long), stream));
   const bool partial = !(x0 == 0 && y0 == 0 && x1 == W && y1 == H && world == 1);
@@ -670,14 +741,8 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   r->last_bpp = opts.pixel_format == RTRB_FMT_RGB8 ? 3 : 4;
 
   // facts needed to finish the stats once the control block has been copied back
-  fc.W = W; fc.H = H; fc.S = S; fc.E = E; fc.n_tiles = n_tiles; fc.detail = opts.count_detail != 0;
-  fc.px_count = 0;
-  for (int b : r->tiles_host) {
-    int tx = b % stx_count, ty = b / stx_count;
-    int ax0 = std::max(x0, tx * RTRB_SUPER), ax1 = std::min(x1, (tx + 1) * RTRB_SUPER);
-    int ay0 = std::max(y0, ty * RTRB_SUPER), ay1 = std::min(y1, (ty + 1) * RTRB_SUPER);
-    if (ax1 > ax0 && ay1 > ay0) fc.px_count += (size_t)(ax1 - ax0) * (ay1 - ay0);
-  }
+  fc.W = W; fc.H = H; fc.S = S; fc.E = E; fc.n_tiles = n_tiles; fc.detail = P.count_detail != 0;
+  fc.px_count = r->tiles_px_count;
   if (stats_out) {
     CUDA_TRY(cudaMemcpyAsync(fc.h, fc.d.p, RTRB_FCB_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
@@ -703,6 +768,8 @@ int finish_stats(rtrb_renderer* r, FrameCtl& fc, rtrb_stats* stats_out) {
   stats_out->cover_sphere_penumbra = c[RTRB_CNT_COV_SPH_PEN];
   stats_out->cover_plane = c[RTRB_CNT_COV_PL]; stats_out->cover_plane_accepts = c[RTRB_CNT_COV_PL_ACC];
   stats_out->adaptive_pixels = c[RTRB_CNT_ADAPTIVE]; stats_out->exact_tests = c[RTRB_CNT_EXACT];
+  stats_out->box_tests = c[RTRB_CNT_BOX_TEST]; stats_out->box_accepts = c[RTRB_CNT_BOX_ACC];
+  stats_out->cover_box = c[RTRB_CNT_COV_BOX]; stats_out->cover_box_accepts = c[RTRB_CNT_COV_BOX_ACC];
   // samples: counted on the device with count_detail; otherwise a pure function of the window
   stats_out->samples = fc.detail ? c[RTRB_CNT_SAMPLES]
                                  : (uint64_t)fc.px_count * fc.S + (uint64_t)(fc.E > 0 ? c[RTRB_CNT_ADAPTIVE] * (uint64_t)fc.E : 0);
@@ -716,9 +783,11 @@ int finish_stats(rtrb_renderer* r, FrameCtl& fc, rtrb_stats* stats_out) {
     stats_out->first_bad_x = stats_out->first_bad_y = -1;
   }
   float ms = 0;
-  CUDA_TRY(cudaEventElapsedTime(&ms, fc.ev0, fc.ev1));
-  stats_out->device_ms = ms;
-  if (fc.n_tiles > 0) {
+  if (fc.timed) {
+    CUDA_TRY(cudaEventElapsedTime(&ms, fc.ev0, fc.ev1));
+    stats_out->device_ms = ms;
+  }
+  if (fc.timed && fc.n_tiles > 0) {
     CUDA_TRY(cudaEventElapsedTime(&ms, fc.evt0, fc.evt1));
     stats_out->trace_ms = ms;
   }
@@ -765,6 +834,7 @@ int rtrb_renderer_create(const rtrb_scene_desc* scene, int device, rtrb_renderer
   cudaError_t ce;
   if ((ce = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (ce = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (ce = cudaStreamCreateWithFlags(&r->ctl_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (ce = cudaEventCreateWithFlags(&r->push_ev, cudaEventDisableTiming)) != cudaSuccess ||
       (ce = cudaEventCreateWithFlags(&r->push_done_ev, cudaEventDisableTiming)) != cudaSuccess ||
       (ce = (cudaError_t)r->main_ctl.init()) != cudaSuccess) {
@@ -781,7 +851,7 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   if (!r) return RTRB_OK;
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
-  r->geom.release(); r->mat.release(); r->lights.release(); r->lens_tab.release();
+  r->geom.release(); r->mat.release(); r->lights.release(); r->lens_tab.release(); r->boxes.release();
   r->bvh.release(); r->light_tab.release();
   r->cull_sph.release(); r->cull_pl.release(); r->sph_index.release(); r->pl_index.release(); r->lights_f.release(); r->tiles.release(); r->samples.release();
   r->extra_samples.release(); r->rgb.release(); r->extra_list.release(); r->hit.release(); r->rgba.release();
@@ -792,6 +862,7 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   if (r->push_done_ev) cudaEventDestroy(r->push_done_ev);
   if (r->stream) cudaStreamDestroy(r->stream);
   if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+  if (r->ctl_stream) cudaStreamDestroy(r->ctl_stream);
   delete r;
   return RTRB_OK;
 }
@@ -871,8 +942,12 @@ int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   // to start the next frame into the other slot meanwhile
   CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, fc.ev1, 0));
   CUDA_TRY(cudaMemcpyAsync(rgba_host, tg.rgba, bytes, cudaMemcpyDeviceToHost, r->copy_stream));
-  CUDA_TRY(cudaMemcpyAsync(fc.h, fc.d.p, RTRB_FCB_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->copy_stream));
   CUDA_TRY(cudaEventRecord(fc.copied, r->copy_stream));
+  // the 200-byte control block travels on its own stream: behind the frame on copy_stream its fixed
+  // latency (~10 us) would be added to every frame of a PCIe-bound sequence
+  CUDA_TRY(cudaStreamWaitEvent(r->ctl_stream, fc.ev1, 0));
+  CUDA_TRY(cudaMemcpyAsync(fc.h, fc.d.p, RTRB_FCB_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->ctl_stream));
+  CUDA_TRY(cudaEventRecord(fc.ctl_copied, r->ctl_stream));
   // (the slot is reused only after rtrb_wait has host-synchronised on `copied`, so no stream wait is needed)
   fc.in_flight = true;
   r->next_ticket = ticket + 1;
@@ -886,6 +961,7 @@ int rtrb_wait(rtrb_renderer* r, int ticket, rtrb_stats* stats_out) {
   if (!fc.in_flight) return fail(RTRB_ERR_INVALID, "ticket %d is not in flight", ticket);
   CUDA_TRY(cudaSetDevice(r->device));
   CUDA_TRY(cudaEventSynchronize(fc.copied));
+  CUDA_TRY(cudaEventSynchronize(fc.ctl_copied));
   fc.in_flight = false;
   rtrb_stats local;
   return finish_stats(r, fc, stats_out ? stats_out : &local);

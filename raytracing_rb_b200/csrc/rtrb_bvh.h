@@ -24,6 +24,7 @@ struct BvhNode {        // 64 B: both child boxes live in the parent, one fetch 
 struct BvhBuildSphere {
   double c[3], r;
   int32_t world_index;
+  int32_t bound_only = 0;  // bounding sphere of a box (rtrb_types.h, cull_sph)
 };
 
 namespace rtrb_bvh {

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 #include "../../include/rtrb_b200.h"
@@ -101,6 +102,7 @@ __device__ __forceinline__ double res53(uint32_t a, uint32_t b) {
 struct HitRec {
   d3 p;        // intersection
   bool dir_in; // :in / :out
+  uint8_t face;  // box only: Box#intersect's data[:index] (box.rb:89)
 };
 
 // Sphere#intersect (sphere.rb:60-85).  d_r = |d|, dn = d / d_r are ray invariants.
@@ -133,6 +135,48 @@ __device__ __forceinline__ bool plane_intersect(const DevGeom& g, d3 o, d3 d, Hi
   return true;
 }
 
+// Box#intersect (box.rb:80-99): Plane#intersect on each of the six faces in order, kept when Plane#get_uv
+// of the hit lies in [-0.5, 0.5]^2, nearest by |hit - origin| with a strict `<` (lowest face wins ties).
+// Returns the winning face or -1.  Not inlined and register-only interface: boxes are rare, and the
+// hot sphere/plane kernels must not pay registers or local memory for this loop.
+static __device__ __noinline__ int box_nearest_face(const DevBox* bx, double ox, double oy, double oz, double dx,
+                                                    double dy, double dz) {
+  const d3 o = mk(ox, oy, oz), d = mk(dx, dy, dz);
+  double nearest = CUDART_INF;
+  int face = -1;
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) {
+    const DevBoxFace& F = bx->f[k];
+    const d3 n = mk(F.nx, F.ny, F.nz), pt = mk(F.px, F.py, F.pz);
+    const double den = dot(n, d);
+    if (den == 0) continue;                    // plane.rb:41
+    const double t = dot(pt - o, n) / den;
+    const d3 ip = o + d * t;
+    if (t < 0) continue;                       // plane.rb:46
+    const d3 rel = ip - pt;
+    const double u = dot(rel, mk(F.lx, F.ly, F.lz)) / F.u_unit;  // plane.rb:82
+    const double v = dot(rel, mk(F.ux, F.uy, F.uz)) / F.v_unit;  // plane.rb:83
+    if (-0.5 <= u && u <= 0.5 && -0.5 <= v && v <= 0.5) {
+      const double dd = norm(ip - o);
+      if (dd < nearest) { nearest = dd; face = k; }
+    }
+  }
+  return face;
+}
+__device__ __forceinline__ bool box_intersect(const DevBox& bx, d3 o, d3 d, HitRec& h) {
+  const int face = box_nearest_face(&bx, o.x, o.y, o.z, d.x, d.y, d.z);
+  if (face < 0) return false;
+  // the winning face's Plane#intersect again: same expressions, same bits
+  const DevBoxFace& F = bx.f[face];
+  const d3 n = mk(F.nx, F.ny, F.nz);
+  const double den = dot(n, d);
+  const double t = dot(mk(F.px, F.py, F.pz) - o, n) / den;
+  h.p = o + d * t;
+  h.dir_in = den < 0;
+  h.face = (uint8_t)face;
+  return true;
+}
+
 // Probe ray of cover_area (world_object.rb:42): from `target` towards the light, unnormalised.
 struct CoverRay {
   d3 target, lp, lt, ltn, tl;
@@ -151,8 +195,10 @@ __device__ __forceinline__ CoverRay make_cover_ray(d3 target, const DevLight& L)
 
 // cover_area of ONE object, exactly as the reference evaluates it:
 // Sphere#cover_area (sphere.rb:28-57) / WorldObject#cover_area (world_object.rb:41-49).
-__device__ __forceinline__ double cover_object_exact(const DevGeom& g, const CoverRay& c, double light_radius,
-                                                     ThreadCtx& ctx) {
+// BOX = false compiles the box branch out (kernels specialised for sphere/plane scenes).
+template <bool BOX = true>
+__device__ __forceinline__ double cover_object_exact(const FrameParams& P, const DevGeom& g, const CoverRay& c,
+                                                     double light_radius, ThreadCtx& ctx) {
   if (g.type == RTRB_OBJ_SPHERE) {
     RTRB_COUNT(ctx, RTRB_CNT_COV_SPH);
     HitRec h;
@@ -177,6 +223,17 @@ __device__ __forceinline__ double cover_object_exact(const DevGeom& g, const Cov
     if (r1 > g.radius) return factor * RTRB_PI * g.radius * g.radius / s1;
     return factor;
   }
+  if constexpr (BOX) {
+    if (g.type == RTRB_OBJ_BOX) {  // WorldObject#cover_area (world_object.rb:41-49) through Box#intersect
+      RTRB_COUNT(ctx, RTRB_CNT_COV_BOX);
+      HitRec h;
+      if (box_intersect(P.boxes[g.aux], c.target, c.lt, h) && dot(h.p - c.lp, c.tl) > 0) {
+        RTRB_COUNT(ctx, RTRB_CNT_COV_BOX_ACC);
+        return 1;
+      }
+      return 0;
+    }
+  }
   RTRB_COUNT(ctx, RTRB_CNT_COV_PL);
   HitRec h;
   double den;
@@ -194,7 +251,7 @@ static __device__ __noinline__ double lit_area(const FrameParams& P, d3 target, 
   double total = 1;
   for (int i = 0; i < P.n_objects; ++i) {
     const DevGeom g = P.geom[i];
-    total -= cover_object_exact(g, c, L.radius, ctx);
+    total -= cover_object_exact(P, g, c, L.radius, ctx);
   }
   return fmax(total, 0.0);
 }
@@ -281,7 +338,7 @@ __device__ __forceinline__ d3 trace_sample(const FrameParams& P, d3 ro, d3 rd, u
     const d3 dn = mk(d.x / d_r, d.y / d_r, d.z / d_r);
     double best = P.max_distance;
     int best_i = -1;
-    HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false;
+    HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false; bh.face = 0;
     for (int i = 0; i < P.n_objects; ++i) {
       const DevGeom g = P.geom[i];
       HitRec h;
@@ -290,6 +347,10 @@ __device__ __forceinline__ d3 trace_sample(const FrameParams& P, d3 ro, d3 rd, u
         RTRB_COUNT(ctx, RTRB_CNT_SPH_TEST);
         ok = sphere_intersect(g, o, d, d_r, dn, h);
         if (ok) RTRB_COUNT(ctx, RTRB_CNT_SPH_ACC);
+      } else if (g.type == RTRB_OBJ_BOX) {
+        RTRB_COUNT(ctx, RTRB_CNT_BOX_TEST);
+        ok = box_intersect(P.boxes[g.aux], o, d, h);
+        if (ok) RTRB_COUNT(ctx, RTRB_CNT_BOX_ACC);
       } else {
         RTRB_COUNT(ctx, RTRB_CNT_PL_TEST);
         double den;
@@ -318,7 +379,9 @@ __device__ __forceinline__ d3 trace_sample(const FrameParams& P, d3 ro, d3 rd, u
       rate = bh.dir_in ? M.refractive_rate : 1.0 / M.refractive_rate;
       can_refract = true;
     } else {
+      // a plane, or the face of a box that was hit (Box#intersect_parameters delegates, box.rb:102-107)
       d3 f = mk(g.nx, g.ny, g.nz);
+      if (g.type == RTRB_OBJ_BOX) { const DevBoxFace& F = P.boxes[g.aux].f[bh.face]; f = mk(F.nx, F.ny, F.nz); }
       double fd = dot(f, d);
       double nfd = -fd;
       double sgn = nfd > 0 ? 1.0 : (nfd < 0 ? -1.0 : 0.0);
@@ -536,16 +599,18 @@ __device__ __forceinline__ void init_ctx(ThreadCtx& ctx, bool detail) {
 }
 
 // FAST64 entry point, defined in rtrb_trace_fast.cuh (only instantiated by that translation unit).
-template <int MAXS, bool BVH>
+template <int MAXS, bool BVH, bool BOX>
 __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
                                                 ThreadCtx& ctx, int* primary_hit);
 
-// MODE: 0 = STRICT, 1 = FAST64 with the linear filter, 2 = FAST64 with the sphere BVH
-template <int MAXS, int MODE>
+// MODE: 0 = STRICT, 1 = FAST64 with the linear filter, 2 = FAST64 with the sphere BVH.
+// BOX: the FAST64 kernels carry the Box code only in their full-counter (DETAIL) variants; scenes with a
+// box are always dispatched there (rtrb_api.cu), so the lean hot kernels stay sphere/plane-only.
+template <int MAXS, int MODE, bool BOX>
 __device__ __forceinline__ d3 trace_dispatch(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
                                              ThreadCtx& ctx, int* primary_hit) {
-  if constexpr (MODE == 2) return trace_sample_fast<MAXS, true>(P, ro, rd, pixel, sample, ctx, primary_hit);
-  else if constexpr (MODE == 1) return trace_sample_fast<MAXS, false>(P, ro, rd, pixel, sample, ctx, primary_hit);
+  if constexpr (MODE == 2) return trace_sample_fast<MAXS, true, BOX>(P, ro, rd, pixel, sample, ctx, primary_hit);
+  else if constexpr (MODE == 1) return trace_sample_fast<MAXS, false, BOX>(P, ro, rd, pixel, sample, ctx, primary_hit);
   else return trace_sample<MAXS>(P, ro, rd, pixel, sample, ctx, primary_hit);
 }
 
@@ -575,7 +640,7 @@ __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
       d3 ro, rd;
       lens_ray(P, x, y, theta, ro, rd);
       int ph;
-      d3 col = trace_dispatch<MAXS, MODE>(P, ro, rd, pixel, j, ctx, &ph);
+      d3 col = trace_dispatch<MAXS, MODE, DETAIL>(P, ro, rd, pixel, j, ctx, &ph);
       RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
       if (P.fuse_resolve) {
         // one sample, positive threshold: mean = s / 1.0 = s and variance = 0 < threshold (camera.rb:80-87)
@@ -616,7 +681,7 @@ __device__ __forceinline__ void trace_extra_body(const FrameParams& P) {
     d3 ro, rd;
     lens_ray(P, x, y, theta, ro, rd);
     int ph;
-    d3 col = trace_dispatch<MAXS, MODE>(P, ro, rd, pixel, j, ctx, &ph);
+    d3 col = trace_dispatch<MAXS, MODE, DETAIL>(P, ro, rd, pixel, j, ctx, &ph);
     RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
     double* out = P.extra_samples + w * 3ull;
     out[0] = col.x; out[1] = col.y; out[2] = col.z;

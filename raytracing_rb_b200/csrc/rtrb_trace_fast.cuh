@@ -60,21 +60,24 @@ __device__ __forceinline__ bool sphere_line_misses(const float4 s, const CullRay
   const float b = fmaf(ocz, r.dz, fmaf(ocy, r.dy, ocx * r.dx));
   const float qx = fmaf(-b, r.dx, ocx), qy = fmaf(-b, r.dy, ocy), qz = fmaf(-b, r.dz, ocz);
   const float m2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
-  const float Rp = s.w + r.E;
+  const float Rp = fabsf(s.w) + r.E;  // sign bit = "bounding sphere of a box"
   return m2 > Rp * Rp;
 }
 
 // Full sphere classification (survivors only). 0 = certainly no hit, 1 = possible hit (lo valid),
 // 2 = certain hit (lo, hi valid).  lo/hi bound Ray#distance(intersection) of Sphere#intersect.
+template <bool BOX = true>
 __device__ __forceinline__ int classify_sphere(const float4 s, const CullRay& r, float& lo, float& hi) {
   const float ocx = s.x - r.ox, ocy = s.y - r.oy, ocz = s.z - r.oz;
   const float b = fmaf(ocz, r.dz, fmaf(ocy, r.dy, ocx * r.dx));
   const float qx = fmaf(-b, r.dx, ocx), qy = fmaf(-b, r.dy, ocy), qz = fmaf(-b, r.dz, ocz);
   const float m2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
-  const float Rp = s.w + r.E;
+  const bool bound_only = BOX && __float_as_int(s.w) < 0;  // a box's bounding sphere: never a certain hit
+  const float R = fabsf(s.w);
+  const float Rp = R + r.E;
   if (m2 > Rp * Rp) return 0;
   const float oc2 = fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx));
-  const float Rm = fmaxf(s.w - r.E, 0.0f);
+  const float Rm = fmaxf(R - r.E, 0.0f);
   const bool outside = oc2 > Rp * Rp;
   const bool inside = oc2 < Rm * Rm;
   if (outside && b < -r.E) return 0;  // centre behind an outside origin: `!from_inner && t < 0`
@@ -97,6 +100,10 @@ __device__ __forceinline__ int classify_sphere(const float4 s, const CullRay& r,
     kind = 1;
   }
   lo = fmaxf(lo, 0.0f);
+  if (bound_only) {  // whatever is inside the sphere is met no earlier than the sphere's entry point
+    kind = 1; hi = 0.0f;
+    if (!outside) lo = 0.0f;
+  }
   if (!(lo == lo) || !(hi == hi)) { lo = 0.0f; kind = 1; }  // NaN anywhere: leave it to the exact test
   return kind;
 }
@@ -151,6 +158,7 @@ static __device__ __noinline__ int closest_hit_scan(const FrameParams& P, d3 o, 
     bool ok;
     double den;
     if (g.type == RTRB_OBJ_SPHERE) ok = sphere_intersect(g, o, d, d_r, dn, h);
+    else if (g.type == RTRB_OBJ_BOX) ok = box_intersect(P.boxes[g.aux], o, d, h);
     else ok = plane_intersect(g, o, d, h, den);
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
     if (ok) {
@@ -236,6 +244,7 @@ __device__ __forceinline__ bool bvh_traverse(const FrameParams& P, const BvhRay&
 }
 
 // World#intersect (world.rb:37-59) = FP32 filter (planes + sphere BVH) + exact test of the survivors.
+template <bool BOX>
 __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx) {
   if (P.n_sph > 0xFFFFF || P.n_pl > 8) return closest_hit_scan(P, o, d, bh, ctx);
@@ -254,7 +263,7 @@ __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d,
     const bool ok = bvh_traverse(P, b, -r.E, tmax, [&](uint32_t k) {
       const float4 s = __ldg(&P.cull_sph[k]);
       float lo, hi;
-      const int kind = classify_sphere(s, r, lo, hi);
+      const int kind = classify_sphere<BOX>(s, r, lo, hi);
       if (kind != 0 && lo <= best_hi) {
         S.push(k);
         if (kind == 2 && hi < best_hi) { best_hi = hi; tmax = hi + r.E; }
@@ -272,14 +281,14 @@ __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d,
   for (int c = 0; c < S.n; ++c) {
     const uint32_t k = S.get(c);
     float lo, hi;
-    const int kind = classify_sphere(__ldg(&P.cull_sph[k]), r, lo, hi);
+    const int kind = classify_sphere<BOX>(__ldg(&P.cull_sph[k]), r, lo, hi);
     if (kind == 0 || !(lo <= best_hi)) continue;
     if (!have_dn) { d_r = norm(d); dn = mk(d.x / d_r, d.y / d_r, d.z / d_r); have_dn = true; }
     const int i = P.sph_index[k];
     const DevGeom g = P.geom[i];
     HitRec h;
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-    if (sphere_intersect(g, o, d, d_r, dn, h)) {
+    if ((BOX && g.type == RTRB_OBJ_BOX) ? box_intersect(P.boxes[g.aux], o, d, h) : sphere_intersect(g, o, d, d_r, dn, h)) {
       const double new_dis = norm(o - h.p);
       if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; bh = h; }
     }
@@ -305,6 +314,7 @@ __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d,
 // An object the probe ray certainly misses (or certainly meets beyond the light) has factor 0, hence
 // cover exactly 0 (sphere.rb:29,45-53 multiply everything by factor; world_object.rb:43-47), and
 // total - 0 == total, so skipping it leaves the running difference bit-identical.
+template <bool BOX>
 __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
   CoverRay c;
   c.target = target;
@@ -328,7 +338,7 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
     const bool ok = bvh_traverse(P, b, -r.E, tmax, [&](uint32_t k) {
       const float4 s = __ldg(&P.cull_sph[k]);
       float lo, hi;
-      const int kind = classify_sphere(s, r, lo, hi);
+      const int kind = classify_sphere<BOX>(s, r, lo, hi);
       if (kind != 0 && !(lo > far)) S.push(k);
     });
     if (!ok) return lit_area(P, target, L, ctx);
@@ -357,7 +367,7 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
     last = best_idx;
     if (best_k >= 0) {  // sphere: the full classification may still prove factor == 0
       float lo, hi;
-      const int kind = classify_sphere(__ldg(&P.cull_sph[best_k]), r, lo, hi);
+      const int kind = classify_sphere<BOX>(__ldg(&P.cull_sph[best_k]), r, lo, hi);
       if (kind == 0 || lo > far) continue;
       if (!have_n) {
         c.lt_r = norm(c.lt);
@@ -366,7 +376,7 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
       }
     }
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-    total -= cover_object_exact(P.geom[best_idx], c, L.radius, ctx);
+    total -= cover_object_exact<BOX>(P, P.geom[best_idx], c, L.radius, ctx);
   }
   return fmax(total, 0.0);
 }
@@ -410,6 +420,7 @@ __device__ __forceinline__ uint32_t line_survivors_light(const FrameParams& P, c
 }
 
 // World#intersect (world.rb:37-59) = FP32 filter over every object + exact test of the survivors.
+template <bool BOX>
 __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx, const bool through_lens) {
   if (P.n_sph > RTRB_APEX_MAX || P.n_pl > 8) return closest_hit_scan(P, o, d, bh, ctx);
@@ -420,7 +431,7 @@ __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3
   if (mask != 0u || P.n_pl > 1) {
     for (uint32_t m = mask; m != 0u; m &= m - 1u) {
       float lo, hi;
-      if (classify_sphere(__ldg(&P.cull_sph[__ffs(m) - 1]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
+      if (classify_sphere<BOX>(__ldg(&P.cull_sph[__ffs(m) - 1]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
     }
     for (int k = 0; k < P.n_pl; ++k) {
       float lo, hi;
@@ -437,14 +448,14 @@ __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3
   for (uint32_t m = mask; m != 0u; m &= m - 1u) {
     const int k = __ffs(m) - 1;
     float lo, hi;
-    const int kind = classify_sphere(__ldg(&P.cull_sph[k]), r, lo, hi);
+    const int kind = classify_sphere<BOX>(__ldg(&P.cull_sph[k]), r, lo, hi);
     if (kind == 0 || !(lo <= best_hi)) continue;
     if (!have_dn) { d_r = norm(d); dn = mk(d.x / d_r, d.y / d_r, d.z / d_r); have_dn = true; }
     const int i = P.sph_index[k];
     const DevGeom g = P.geom[i];
     HitRec h;
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-    if (sphere_intersect(g, o, d, d_r, dn, h)) {
+    if ((BOX && g.type == RTRB_OBJ_BOX) ? box_intersect(P.boxes[g.aux], o, d, h) : sphere_intersect(g, o, d, d_r, dn, h)) {
       const double new_dis = norm(o - h.p);
       if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; bh = h; }
     }
@@ -470,6 +481,7 @@ __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3
 // An object the probe ray certainly misses (or certainly meets beyond the light) has factor 0, hence
 // cover exactly 0 (sphere.rb:29,45-53 multiply everything by factor; world_object.rb:43-47), and
 // total - 0 == total, so skipping it leaves the running difference bit-identical.
+template <bool BOX>
 __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 target, const DevLight& L, const int light_index,
                                                   ThreadCtx& ctx) {
   CoverRay c;
@@ -503,7 +515,7 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
     if (is < iq) {
       sm &= sm - 1u;
       float lo, hi;
-      const int kind = classify_sphere(__ldg(&P.cull_sph[ks]), r, lo, hi);
+      const int kind = classify_sphere<BOX>(__ldg(&P.cull_sph[ks]), r, lo, hi);
       if (kind == 0 || lo > far) continue;
       if (!have_n) {
         c.lt_r = norm(c.lt);
@@ -511,11 +523,11 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
         have_n = true;
       }
       RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-      total -= cover_object_exact(P.geom[is], c, L.radius, ctx);
+      total -= cover_object_exact<BOX>(P, P.geom[is], c, L.radius, ctx);
     } else {
       qm &= qm - 1u;
       RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-      total -= cover_object_exact(P.geom[iq], c, L.radius, ctx);
+      total -= cover_object_exact<BOX>(P, P.geom[iq], c, L.radius, ctx);
     }
   }
   return fmax(total, 0.0);
@@ -523,17 +535,17 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
 
 // Compile-time choice: kernels are instantiated once per filter so each stays compact (the linear
 // scan wins below ~32 spheres: measured 5.56 vs 6.05 ms on config 3; the BVH wins 5x on config 5).
-template <bool BVH>
+template <bool BVH, bool BOX>
 __device__ __forceinline__ int closest_hit_fast(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx, const bool through_lens) {
-  if constexpr (BVH) return closest_hit_bvh(P, o, d, r, bh, ctx);
-  else return closest_hit_linear(P, o, d, r, bh, ctx, through_lens);
+  if constexpr (BVH) return closest_hit_bvh<BOX>(P, o, d, r, bh, ctx);
+  else return closest_hit_linear<BOX>(P, o, d, r, bh, ctx, through_lens);
 }
-template <bool BVH>
+template <bool BVH, bool BOX>
 __device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target, const DevLight& L, const int light_index,
                                                 ThreadCtx& ctx) {
-  if constexpr (BVH) return lit_area_bvh(P, target, L, ctx);
-  else return lit_area_linear(P, target, L, light_index, ctx);
+  if constexpr (BVH) return lit_area_bvh<BOX>(P, target, L, ctx);
+  else return lit_area_linear<BOX>(P, target, L, light_index, ctx);
 }
 
 // World#high_lights match for one light (world.rb:86-93): acos(|cos|) < threshold, filtered in FP32 on
@@ -569,7 +581,7 @@ __device__ __forceinline__ bool attenuation_dead(d3 att) {
 
 // rt_map (ray_tracer.rb:50-164) for ONE popped work item, FAST64 evaluation: pushes the children
 // onto `stack`, adds the emitted colours to `sum` in emission order.
-template <int MAXS, bool BVH>
+template <int MAXS, bool BVH, bool BOX>
 __device__ __forceinline__ void process_item_fast(const FrameParams& P, const StackItem& it, StackItem* stack, int& sp,
                                                   d3& sum, ThreadCtx& ctx, uint32_t pixel, uint32_t sample,
                                                   bool is_first, int* primary_hit) {
@@ -602,8 +614,8 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
     }
 
     // ---- World#intersect ----
-    HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false;
-    const int best_i = closest_hit_fast<BVH>(P, o, d, r, bh, ctx, is_first);
+    HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false; bh.face = 0;
+    const int best_i = closest_hit_fast<BVH, BOX>(P, o, d, r, bh, ctx, is_first);
     if (best_i < 0) return;
     if (is_first) *primary_hit = best_i;
     RTRB_COUNT(ctx, RTRB_CNT_HITS);
@@ -620,7 +632,11 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
       rate = bh.dir_in ? M.refractive_rate : 1.0 / M.refractive_rate;
       can_refract = true;
     } else {
+      // a plane, or the face of a box that was hit (Box#intersect_parameters delegates, box.rb:102-107)
       d3 f = mk(g.nx, g.ny, g.nz);
+      if constexpr (BOX) {
+        if (g.type == RTRB_OBJ_BOX) { const DevBoxFace& F = P.boxes[g.aux].f[bh.face]; f = mk(F.nx, F.ny, F.nz); }
+      }
       double fd = dot(f, d);
       double nfd = -fd;
       double sgn = nfd > 0 ? 1.0 : (nfd < 0 ? -1.0 : 0.0);
@@ -630,7 +646,7 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
       can_refract = M.has_refraction != 0;
     }
     d3 nn;
-    if (g.type != RTRB_OBJ_SPHERE && M.plane_nn_valid) {
+    if ((BOX ? g.type == RTRB_OBJ_PLANE : g.type != RTRB_OBJ_SPHERE) && M.plane_nn_valid) {
       // n is +-front: its normalisation is a per-plane constant baked on the host (-(x / r) == (-x) / r)
       const d3 pn = ld3(M.plane_nn);
       nn = (n.x == g.nx && n.y == g.ny && n.z == g.nz) ? pn : -pn;
@@ -703,7 +719,7 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
     for (int l = 0; l < P.n_lights; ++l) {
       const DevLight& L = P.lights[l];
       ctx.shadow++;
-      const double area = lit_area_fast<BVH>(P, shade_from, L, l, ctx);
+      const double area = lit_area_fast<BVH, BOX>(P, shade_from, L, l, ctx);
       if (area > 0) {
         double w = rb_pow(area, P.soft_shadow_exponent);
         if (P.n_lights != 1) w = w / (double)P.n_lights;  // x / 1.0 == x
@@ -773,7 +789,7 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
 }
 
 // RayTracer#trace_sync for one sample (non-persistent form; used by tools and kept for reference).
-template <int MAXS, bool BVH>
+template <int MAXS, bool BVH, bool BOX>
 __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
                                                 ThreadCtx& ctx, int* primary_hit) {
   StackItem stack[MAXS > 1 ? MAXS : 1];
@@ -789,7 +805,7 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
   *primary_hit = -1;
   ctx.max_stack = max(ctx.max_stack, 1u);
   while (true) {
-    process_item_fast<MAXS, BVH>(P, it, stack, sp, sum, ctx, pixel, sample, first, primary_hit);
+    process_item_fast<MAXS, BVH, BOX>(P, it, stack, sp, sum, ctx, pixel, sample, first, primary_hit);
     first = false;
     if (MAXS == 1 || sp == 0) break;
     if ((uint32_t)sp > ctx.max_stack) ctx.max_stack = (uint32_t)sp;

@@ -22,8 +22,19 @@ struct DevGeom {      // 64 B
   double radius;      // sphere radius (0 for planes)
   double nx, ny, nz;  // plane front (unnormalised, as the reference keeps it)
   int32_t type;       // RTRB_OBJ_*
-  int32_t pad;
+  int32_t aux;        // box: index into FrameParams::boxes
 };
+
+// One bounded face of a Box (box.rb:22-73): a Plane.create_from_scratch with front / up / point / units
+// assigned, `left` from Plane#reinit (plane.rb:21-23), and the two unit vectors Plane#get_uv forms.
+struct DevBoxFace {   // 112 B
+  double px, py, pz;  // point
+  double nx, ny, nz;  // front (unnormalised)
+  double lx, ly, lz;  // normalize(normalize(front x up))   plane.rb:22,82
+  double ux, uy, uz;  // normalize(up)                      plane.rb:83
+  double u_unit, v_unit;
+};
+struct DevBox { DevBoxFace f[6]; };  // up, bottom, front, back, left, right (box.rb:60-65)
 
 struct DevMat {
   double diffuse[3], refl[3], refr[3], ambient[3];
@@ -78,8 +89,10 @@ struct FrameParams {
   const DevGeom* geom;
   const DevMat* mat;
   const DevLight* lights;
+  const DevBox* boxes;         // [n_boxes], indexed by DevGeom::aux
   // FP32 filter view (FAST64): spheres and planes split by type, original indices kept
-  const float4* cull_sph;      // [n_sph] (cx, cy, cz, R)
+  const float4* cull_sph;      // [n_sph] (cx, cy, cz, R); sign bit of R set = bounding sphere of a box:
+                               //         the line test applies, "certain hit" conclusions do not
   const int32_t* sph_index;    // [n_sph] index in world_objects
   const float4* cull_pl;       // [2*n_pl] (nx, ny, nz, |n|_1), (px, py, pz, |P|_inf)
   const int32_t* pl_index;     // [n_pl]
@@ -128,7 +141,8 @@ enum {
   RTRB_CNT_SAMPLES = 0, RTRB_CNT_RAYS, RTRB_CNT_SHADOW, RTRB_CNT_HIGHLIGHT, RTRB_CNT_HITS, RTRB_CNT_LOCAL,
   RTRB_CNT_LIT, RTRB_CNT_MC, RTRB_CNT_REFR, RTRB_CNT_TEXEL, RTRB_CNT_SPH_TEST, RTRB_CNT_SPH_ACC,
   RTRB_CNT_PL_TEST, RTRB_CNT_PL_ACC, RTRB_CNT_COV_SPH, RTRB_CNT_COV_SPH_FULL, RTRB_CNT_COV_SPH_PEN,
-  RTRB_CNT_COV_PL, RTRB_CNT_COV_PL_ACC, RTRB_CNT_ADAPTIVE, RTRB_CNT_EXACT, RTRB_CNT_N
+  RTRB_CNT_COV_PL, RTRB_CNT_COV_PL_ACC, RTRB_CNT_ADAPTIVE, RTRB_CNT_EXACT,
+  RTRB_CNT_BOX_TEST, RTRB_CNT_BOX_ACC, RTRB_CNT_COV_BOX, RTRB_CNT_COV_BOX_ACC, RTRB_CNT_N
 };
 
 // Morton decode of the 10-bit in-super-tile index q: even bits -> x, odd bits -> y, so that 32

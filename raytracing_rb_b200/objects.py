@@ -1,5 +1,5 @@
-"""Mirror of Alex::Objects::{WorldObject,Sphere,Plane} (reference src/objects/world_object.rb:8-18,
-sphere.rb:6-26, plane.rb:7-36) as HOST-side property bags: same attribute names, same derived
+"""Mirror of Alex::Objects::{WorldObject,Sphere,Plane,Box} (reference src/objects/world_object.rb:8-18,
+sphere.rb:6-26, plane.rb:7-36, box.rb:9-74) as HOST-side property bags: same attribute names, same derived
 vectors, same mandatory-in-practice keys.  Their per-ray methods (intersect, cover_area,
 local_lighting, ...) are the CUDA kernels' job; `to_desc` flattens one object for the C ABI."""
 from . import _abi
@@ -114,7 +114,7 @@ class Plane(WorldObject):  # plane.rb
         what = "Plane(%s)" % self.name
         d.type = self.TYPE
         d.texture = texture_index
-        d.has_refraction = 1 if self.refractive_rate else 0  # plane.rb:57 `if self.refractive_rate`
+        d.has_refraction = 1 if self.refractive_rate is not None else 0  # plane.rb:57 `if self.refractive_rate` (0.0 is truthy in Ruby)
         d.point = _v(self.point, what + ".point")
         d.front = _v(self.front, what + ".front")
         d.up = _v(self.up, what + ".up")
@@ -132,4 +132,56 @@ class Plane(WorldObject):  # plane.rb
         return d
 
 
-OBJECT_CLASSES = {"Sphere": Sphere, "Plane": Plane}  # world.rb:31 `eval("Alex::Objects::#{type}")`
+class Box(WorldObject):  # box.rb
+    """Six bounded faces (box.rb:22-73).  The faces are Plane.create_from_scratch objects carrying only
+    what Box#initialize assigns; they are rebuilt here for introspection (`planes`), while the device
+    derives its own copy from the same nine numbers in the reference's evaluation order."""
+    TYPE = _abi.OBJ_BOX
+    point = front = up = None
+    width_front = width_up = width_left = None
+
+    def __init__(self, properties=None, config_path=None):
+        super().__init__(properties, config_path)
+        if self.texture_file_path:  # box.rb:17-19: decoded, but Box never samples it (no local_lighting override)
+            self.texture = Texture(self.texture_file_path, self.texture_horizontal_scale, self.texture_vertical_scale,
+                                   config_path=self._config_path)
+        left = self.front.cross(self.up).normalize()  # box.rb:23 (raises on a zero vector like the reference)
+        wf, wu, wl = float(self.width_front), float(self.width_up), float(self.width_left)
+        spec = [  # (front, up, point, u_unit, v_unit), box.rb:25-59
+            (self.up, left, self.point + self.up * wu * 0.5, wf, wl),
+            (-self.up, left, self.point - self.up * wu * 0.5, wf, wl),
+            (self.front, self.up, self.point + self.front * wf * 0.5, wl, wu),
+            (-self.front, self.up, self.point - self.front * wf * 0.5, wl, wu),
+            (left, self.up, self.point + left * wl * 0.5, wf, wu),
+            (-left, self.up, self.point - left * wl * 0.5, wf, wu),
+        ]
+        self.planes = []
+        for f, u, pt, uu, vu in spec:
+            p = Plane.create_from_scratch()
+            p.front, p.up, p.point, p.u_unit, p.v_unit = f, u, pt, uu, vu
+            p.reflective_attenuation = self.reflective_attenuation  # box.rb:66-72
+            p.refractive_attenuation = self.refractive_attenuation
+            p.refractive_rate = self.refractive_rate
+            p.diffuse_rate = self.diffuse_rate
+            p.reinit()
+            self.planes.append(p)
+
+    def to_desc(self, texture_index):
+        d = _abi.ObjectDesc()
+        what = "Box(%s)" % self.name
+        d.type = self.TYPE
+        d.texture = -1  # WorldObject#local_lighting runs without a colour filter for boxes
+        d.has_refraction = 1 if self.refractive_rate is not None else 0  # plane.rb:57 on every face
+        d.point = _v(self.point, what + ".point")
+        d.front = _v(self.front, what + ".front")
+        d.up = _v(self.up, what + ".up")
+        d.width_front = _f(self.width_front, what + ".width_front")
+        d.width_up = _f(self.width_up, what + ".width_up")
+        d.width_left = _f(self.width_left, what + ".width_left")
+        if d.has_refraction:
+            d.refractive_rate = float(self.refractive_rate)
+        self._material_into(d)
+        return d
+
+
+OBJECT_CLASSES = {"Sphere": Sphere, "Plane": Plane, "Box": Box}  # world.rb:31 `eval("Alex::Objects::#{type}")`

@@ -146,13 +146,50 @@ def config5(width=3840, height=2160, spp=64, grid=32):
                     trace_depth=8, monte_carlo_diffusion_times=0))
 
 
-CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}
+def box(name, point, front, up, widths, glassy=True):
+    """A Box in the reference's world.yml format (config/world.yml:114-129, commented out upstream)."""
+    p = {"name": name, "point": [float(v) for v in point], "front": [float(v) for v in front],
+         "up": [float(v) for v in up], "width_front": float(widths[0]), "width_up": float(widths[1]),
+         "width_left": float(widths[2]), "ambient": _c3(0.01)}
+    if glassy:  # the upstream "big box" material
+        p.update({"refractive_rate": 1.1, "reflective_attenuation": _c3(0.1), "refractive_attenuation": _c3(0.4),
+                  "diffuse_rate": _c3(0.4)})
+    else:       # no refractive_rate key: the faces never refract (plane.rb:57)
+        p.update({"reflective_attenuation": _c3(0.3), "diffuse_rate": [0.5, 0.6, 0.3]})
+    return {"type": "Box", "properties": p}
+
+
+def config6(width=192, height=108):
+    """the reference default scene with its commented-out `big box`
+    (config/world.yml:114-129) switched on, plus a matte box lying on the ground near the camera."""
+    w, c = config1()
+    w = copy.deepcopy(w)
+    w["world_objects"].append(box("big box", [10, -2.2, 1], [1, 0, 0], [0, 0, 1], (0.4, 4.0, 0.4)))
+    w["world_objects"].append(box("crate", [6, 1.5, -0.6], [1, 1, 0], [0, 0, 1], (0.9, 0.8, 1.3), glassy=False))
+    c = dict(c, width=width, height=height)
+    return w, c
+
+
+def config7(width=480, height=270, spp=2, grid=8):
+    """Boxes among many spheres (the BVH filter path, > 32 bounded objects): a glass box, a matte box and a
+    skewed box whose `up` is not perpendicular to `front` (no filter bound: always exact-tested)."""
+    w, c = config5(width=width, height=height, spp=spp, grid=grid)
+    objs = w["world_objects"]
+    objs.insert(5, box("glass slab", [9, -3, 0.2], [1, 0.3, 0], [0, 0, 1], (0.6, 2.4, 1.8)))
+    objs.insert(20, box("crate", [14, 4, -0.5], [0, 1, 0], [0, 0, 1], (1.5, 1.0, 1.5), glassy=False))
+    objs.append(box("skewed", [7, 2.5, -0.4], [1, 0, 0.2], [0, 0.1, 1], (1.0, 1.2, 0.8), glassy=False))
+    return w, dict(c, trace_depth=5)
+
+
+CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5, 6: config6, 7: config7}
 NAMES = {
     1: "config1: reference default scene 192x108 (adaptive 3..10 spp, depth 4, mc 1)",
     2: "config2: 1920x1080 ground + 16 matte spheres, hard shadows, 1 spp, depth 1",
     3: "config3: 1920x1080 depth 8, textured sphere + wall, glass, 4 spp",
     4: "config4: 1920x1080 soft shadows r=0.8, 16 spp, depth 4, mc 1",
     5: "config5: 3840x2160 1024 spheres, depth 8, 64 spp",
+    6: "config6: reference default scene + its commented-out Box (world.yml:114-129) + a matte box",
+    7: "config7: boxes among 64 spheres (BVH filter), depth 5",
 }
 
 

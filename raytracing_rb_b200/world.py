@@ -50,7 +50,7 @@ class World(ConfigurableObject):
         objs = (_abi.ObjectDesc * max(1, len(self.world_objects)))()
         for i, o in enumerate(self.world_objects):
             ti = -1
-            if o.texture is not None:
+            if o.texture is not None and getattr(o, "TYPE", None) != _abi.OBJ_BOX:
                 key = o.texture.file_name
                 if key not in tex_index:
                     tex_index[key] = len(textures)

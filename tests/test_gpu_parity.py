@@ -77,6 +77,8 @@ def test_config5_many_spheres(oracle_mod, precision):
     (3, {}),                                    # full 1920x1080, depth 8, 4 spp, glass + textures
     (4, dict(width=960, height=540)),           # soft shadows + MC rays
     (5, dict(width=480, height=270, spp=4)),    # 1024 spheres
+    (6, dict(width=960, height=540)),           # default scene + boxes (linear filter, box bounding spheres)
+    (7, dict(width=960, height=540)),           # boxes among 64 spheres (BVH filter), one box without a bound
 ])
 def test_fast64_is_bit_identical_to_strict(config_id, kw):
     """Size-independent property used at BASELINE sizes, where the CPU oracle is too slow: the FP32
@@ -215,3 +217,60 @@ def test_depth1_with_mc_rays(oracle_mod, precision):
     got = cam.render_frame(seed=9, precision=precision, count_detail=True)
     check(ref, got, precision == PREC_STRICT)
     assert got.stats["mc_rays"] == ref.stats["mc_rays"] > 0
+
+
+BOX_COUNTERS = ("box_tests", "box_accepts", "cover_box", "cover_box_accepts")
+
+
+@pytest.mark.parametrize("precision", [PREC_STRICT, PREC_FAST64])
+@pytest.mark.parametrize("config_id,kw", [(6, {}), (7, dict(width=160, height=90))])
+def test_box_scenes(oracle_mod, config_id, kw, precision):
+    """the Box primitive (box.rb) against the oracle - image, primary hit ids (boxes are
+    hit), ray counters; STRICT additionally reproduces the per-object test counters."""
+    ref, got = run_both(oracle_mod, config_id, precision, **kw)
+    check(ref, got, precision == PREC_STRICT)
+    world, _ = load_scene(config_id, **kw)
+    from raytracing_rb_b200 import Box
+    box_ids = [i for i, o in enumerate(world.world_objects) if isinstance(o, Box)]
+    assert box_ids and np.isin(got.hit, box_ids).sum() > 0
+    if precision == PREC_STRICT:
+        for k in BOX_COUNTERS:
+            assert got.stats[k] == ref.stats[k] > 0, k
+
+
+def test_rgb8_frame_is_rgba8_without_alpha():
+    """RTRB_FMT_RGB8: the same bytes minus the constant alpha, through the blocking call and through
+    rtrb_submit / rtrb_wait."""
+    import torch
+    from raytracing_rb_b200 import _abi
+    world, cam = load_scene(3, width=200, height=120)
+    r, c = cam.renderer(), cam.camera_desc()
+    a = r.render(c, make_opts(seed=4), want_rgb=False, want_hit=False)
+    b = r.render(c, make_opts(seed=4, pixel_format=_abi.FMT_RGB8), want_rgb=False, want_hit=False)
+    assert b.rgba.shape == (120, 200, 3)
+    assert np.array_equal(a.rgba[..., :3], b.rgba)
+    buf = torch.zeros((120, 200, 3), dtype=torch.uint8).pin_memory().numpy()
+    st, _ = r.wait(r.submit(c, buf, make_opts(seed=4, pixel_format=_abi.FMT_RGB8)))
+    assert np.array_equal(buf, b.rgba) and st["rays"] == a.stats["rays"]
+    assert st["device_ms"] == 0.0  # pipelined frames are not timed
+
+
+def test_peer_push_carries_a_frame_between_renderers():
+    """rtrb_peer_push / rtrb_peer_push_join (copy-engine gather): a frame rendered by one renderer lands in
+    a frame slot of another renderer's framebuffer (same GPU here; a peer mapping on a multi-GPU box)."""
+    world, cam = load_scene(2, width=320, height=180)
+    from raytracing_rb_b200 import Renderer
+    src, dst = cam.renderer(), Renderer(world.to_scene_desc(), 0)
+    c = cam.camera_desc()
+    W, H = 320, 180
+    want = src.render(c, make_opts(seed=1), want_rgb=False, want_hit=False).rgba
+    sp = src.framebuffer_ptr(W, H)
+    dp = dst.framebuffer_ptr(W, H * 3)
+    src.render_device(c, make_opts(seed=1), want_stats=False)
+    src.peer_push(sp, dp + 2 * W * H * 4, W * H * 4)
+    src.peer_push_join()
+    src.render_device(c, make_opts(seed=1))  # stats => synchronises the stream the join was queued on
+    out = np.zeros((H * 3, W, 4), np.uint8)
+    dst.framebuffer_download(W, H * 3, out)
+    assert np.array_equal(out[2 * H:], want)
+    assert not out[:2 * H].any()
