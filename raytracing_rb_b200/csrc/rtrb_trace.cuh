@@ -246,12 +246,13 @@ __device__ __forceinline__ double cover_object_exact(const FrameParams& P, const
 
 // World#lit_area (world.rb:62-69) for one light seen from `target`:
 // max(1 - sum over ALL objects of cover_area, 0), subtraction in world_objects order.
+template <bool BOX = true>
 static __device__ __noinline__ double lit_area(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
   const CoverRay c = make_cover_ray(target, L);
   double total = 1;
   for (int i = 0; i < P.n_objects; ++i) {
     const DevGeom g = P.geom[i];
-    total -= cover_object_exact(P, g, c, L.radius, ctx);
+    total -= cover_object_exact<BOX>(P, g, c, L.radius, ctx);
   }
   return fmax(total, 0.0);
 }

@@ -73,7 +73,7 @@ __device__ __forceinline__ int classify_sphere(const float4 s, const CullRay& r,
   const float qx = fmaf(-b, r.dx, ocx), qy = fmaf(-b, r.dy, ocy), qz = fmaf(-b, r.dz, ocz);
   const float m2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
   const bool bound_only = BOX && __float_as_int(s.w) < 0;  // a box's bounding sphere: never a certain hit
-  const float R = fabsf(s.w);
+  const float R = BOX ? fabsf(s.w) : s.w;
   const float Rp = R + r.E;
   if (m2 > Rp * Rp) return 0;
   const float oc2 = fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx));
@@ -130,6 +130,13 @@ __device__ __forceinline__ int classify_plane(const float4 a, const float4 p, co
   return (t - e_t > 0.0f) ? 2 : 1;
 }
 
+// bh = h; the face byte only exists for kernels that carry the Box code
+template <bool BOX>
+__device__ __forceinline__ void keep_hit(HitRec& bh, const HitRec& h) {
+  bh.p = h.p; bh.dir_in = h.dir_in;
+  if constexpr (BOX) bh.face = h.face;
+}
+
 // Up to 8 survivor slots of 16 bits each, kept in two registers (no local-memory array).
 struct Pack8 {
   unsigned long long a, b;
@@ -147,6 +154,7 @@ struct Pack8 {
 };
 
 // The reference's own scan (world.rb:44-57); used when the filter keeps more survivors than fit.
+template <bool BOX>
 static __device__ __noinline__ int closest_hit_scan(const FrameParams& P, d3 o, d3 d, HitRec& bh, ThreadCtx& ctx) {
   const double d_r = norm(d);
   const d3 dn = mk(d.x / d_r, d.y / d_r, d.z / d_r);
@@ -158,12 +166,12 @@ static __device__ __noinline__ int closest_hit_scan(const FrameParams& P, d3 o, 
     bool ok;
     double den;
     if (g.type == RTRB_OBJ_SPHERE) ok = sphere_intersect(g, o, d, d_r, dn, h);
-    else if (g.type == RTRB_OBJ_BOX) ok = box_intersect(P.boxes[g.aux], o, d, h);
+    else if (BOX && g.type == RTRB_OBJ_BOX) ok = box_intersect(P.boxes[g.aux], o, d, h);
     else ok = plane_intersect(g, o, d, h, den);
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
     if (ok) {
       const double new_dis = norm(o - h.p);
-      if (new_dis < best) { best = new_dis; best_i = i; bh = h; }
+      if (new_dis < best) { best = new_dis; best_i = i; keep_hit<BOX>(bh, h); }
     }
   }
   return best_i;
@@ -247,7 +255,7 @@ __device__ __forceinline__ bool bvh_traverse(const FrameParams& P, const BvhRay&
 template <bool BOX>
 __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx) {
-  if (P.n_sph > 0xFFFFF || P.n_pl > 8) return closest_hit_scan(P, o, d, bh, ctx);
+  if (P.n_sph > 0xFFFFF || P.n_pl > 8) return closest_hit_scan<BOX>(P, o, d, bh, ctx);
   // pass 1a: planes bound the search first (nothing at or beyond max_distance can win, world.rb:39)
   float best_hi = P.max_distance_f;
   for (int k = 0; k < P.n_pl; ++k) {
@@ -269,7 +277,7 @@ __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d,
         if (kind == 2 && hi < best_hi) { best_hi = hi; tmax = hi + r.E; }
       }
     });
-    if (!ok || S.overflow()) return closest_hit_scan(P, o, d, bh, ctx);
+    if (!ok || S.overflow()) return closest_hit_scan<BOX>(P, o, d, bh, ctx);
   }
   // pass 2: exact FP64 evaluation of whatever can still win; (distance, index) lexicographic order
   // reproduces the strict `<` scan in world_objects order.
@@ -290,7 +298,7 @@ __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d,
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
     if ((BOX && g.type == RTRB_OBJ_BOX) ? box_intersect(P.boxes[g.aux], o, d, h) : sphere_intersect(g, o, d, d_r, dn, h)) {
       const double new_dis = norm(o - h.p);
-      if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; bh = h; }
+      if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; keep_hit<BOX>(bh, h); }
     }
   }
   for (int k = 0; k < P.n_pl; ++k) {
@@ -304,7 +312,7 @@ __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d,
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
     if (plane_intersect(g, o, d, h, den)) {
       const double new_dis = norm(o - h.p);
-      if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; bh = h; }
+      if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; keep_hit<BOX>(bh, h); }
     }
   }
   return best_i;
@@ -328,7 +336,7 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
     const float lx = (float)c.lt.x, ly = (float)c.lt.y, lz = (float)c.lt.z;
     far = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) * 1.00001f + 2.0f * r.E;
   }
-  if (P.n_sph > 0xFFFFF || P.n_pl > 0xFFFF) return lit_area(P, target, L, ctx);
+  if (P.n_sph > 0xFFFFF || P.n_pl > 0xFFFF) return lit_area<BOX>(P, target, L, ctx);
   Pack8 S, Q;
   S.clear();
   Q.clear();
@@ -341,14 +349,14 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
       const int kind = classify_sphere<BOX>(s, r, lo, hi);
       if (kind != 0 && !(lo > far)) S.push(k);
     });
-    if (!ok) return lit_area(P, target, L, ctx);
+    if (!ok) return lit_area<BOX>(P, target, L, ctx);
   }
   for (int k = 0; k < P.n_pl; ++k) {
     float lo, hi;
     const int kind = classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi);
     if (kind != 0 && !(lo > far)) Q.push((uint32_t)k);
   }
-  if (S.overflow() || Q.overflow()) return lit_area(P, target, L, ctx);
+  if (S.overflow() || Q.overflow()) return lit_area<BOX>(P, target, L, ctx);
   double total = 1;
   bool have_n = false;
   // visit the survivors in ascending world_objects index (selection over <= 16 entries)
@@ -423,7 +431,7 @@ __device__ __forceinline__ uint32_t line_survivors_light(const FrameParams& P, c
 template <bool BOX>
 __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx, const bool through_lens) {
-  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > 8) return closest_hit_scan(P, o, d, bh, ctx);
+  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > 8) return closest_hit_scan<BOX>(P, o, d, bh, ctx);
   const uint32_t mask = (through_lens && P.cam_tab_valid) ? line_survivors_camera(P, r) : line_survivors_generic(P, r);
   // pass 1 (only when something can be pruned): the smallest certain upper bound; nothing at or beyond
   // max_distance can win (world.rb:39)
@@ -457,7 +465,7 @@ __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
     if ((BOX && g.type == RTRB_OBJ_BOX) ? box_intersect(P.boxes[g.aux], o, d, h) : sphere_intersect(g, o, d, d_r, dn, h)) {
       const double new_dis = norm(o - h.p);
-      if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; bh = h; }
+      if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; keep_hit<BOX>(bh, h); }
     }
   }
   for (int k = 0; k < P.n_pl; ++k) {
@@ -471,7 +479,7 @@ __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
     if (plane_intersect(g, o, d, h, den)) {
       const double new_dis = norm(o - h.p);
-      if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; bh = h; }
+      if (new_dis < best || (new_dis == best && best_i >= 0 && i < best_i)) { best = new_dis; best_i = i; keep_hit<BOX>(bh, h); }
     }
   }
   return best_i;
@@ -496,7 +504,7 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
     const float lx = (float)c.lt.x, ly = (float)c.lt.y, lz = (float)c.lt.z;
     far = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) * 1.00001f + 2.0f * r.E;
   }
-  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > 32) return lit_area(P, target, L, ctx);
+  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > 32) return lit_area<BOX>(P, target, L, ctx);
   // the probe ray's line passes through the light: apex table of this light when there is one
   uint32_t sm = (P.light_tab != nullptr) ? line_survivors_light(P, light_index, r) : line_survivors_generic(P, r);
   uint32_t qm = 0u;
@@ -614,7 +622,8 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
     }
 
     // ---- World#intersect ----
-    HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false; bh.face = 0;
+    HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false;
+    if constexpr (BOX) bh.face = 0;
     const int best_i = closest_hit_fast<BVH, BOX>(P, o, d, r, bh, ctx, is_first);
     if (best_i < 0) return;
     if (is_first) *primary_hit = best_i;
