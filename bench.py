@@ -184,7 +184,19 @@ def run_ours(args, rank, local_rank, world_size):
     if world_size > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on STDOUT when the first communicator is built; stdout must carry
+        # exactly one JSON line, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     precision = PREC_STRICT if args.precision == "strict" else PREC_FAST64
     fmt = _abi.FMT_RGB8 if args.pixel_format == "rgb8" else _abi.FMT_RGBA8
     bpp = 3 if fmt == _abi.FMT_RGB8 else 4
@@ -428,7 +440,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="480x270 variant for quick checks (not a bench value)")
     ap.add_argument("--pixel-format", default="rgb8", choices=["rgb8", "rgba8"],
                     help="8-bit frame layout delivered (rgb8: alpha is the constant 255 and stays off the wire)")
-    ap.add_argument("--gather", default="store", choices=["store", "copy"],
+    ap.add_argument("--gather", default="copy", choices=["store", "copy"],
                     help="N > 1: how finished frames reach rank 0's slots (peer stores from the kernel / copy engine)")
     ap.add_argument("--tile-split", action="store_true",
                     help="N > 1: cut every frame into super-tiles across the ranks (strong scaling of heavy frames)")
