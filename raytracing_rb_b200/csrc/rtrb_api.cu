@@ -95,8 +95,8 @@ struct DevBuf {
 
 // Frame control block: every small per-frame device word in ONE buffer (one memset, one D2H copy).
 // u64 words: [0, RTRB_CNT_N) counters | [N] first_bad | [N+1, N+2] work claims | [N+3] = {status, max_stack}
-// | [N+4] = {extra_count, pad}
-#define RTRB_FCB_WORDS (RTRB_CNT_N + 5)
+// | [N+4] = {extra_count, pad} | [N+5, N+5+2*RTRB_HOT_SLICES) sliced (rays, shadow) counters
+#define RTRB_FCB_WORDS (RTRB_CNT_N + 5 + 2 * RTRB_HOT_SLICES)
 #define RTRB_PIPE_SLOTS 4  // frames that may be in flight between rtrb_submit and rtrb_wait
 struct FrameCtl {
   DevBuf<unsigned long long> d;
@@ -154,6 +154,7 @@ struct rtrb_renderer {
   DevBuf<int32_t> tiles;
   std::vector<int32_t> tiles_host;     // global ids ty * stx_count + tx
   size_t tiles_px_count = 0;           // pixels of the window covered by tiles_host
+  uint32_t tiles_magic = 0;            // see FrameParams::tiles_magic (0 when the list is not plain row-major)
   DevBuf<double> lens_tab;             // [W + H] per-column / per-row retina offsets
   double lens_key[4] = {0, 0, 0, 0};   // (W, H, retina_width, retina_height) the table was built for
   int tiles_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
@@ -632,6 +633,16 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     }
     CUDA_TRY(cudaStreamSynchronize(stream));
     memcpy(r->tiles_key, key, sizeof(key));
+    r->tiles_magic = 0;
+    if (stx_count > 0 && stx_count < 65536 && r->tiles_host.size() < 65536) {
+      const uint32_t magic = (uint32_t)((1ull << 32) / (unsigned)stx_count) + 1u;
+      bool ok = true;
+      for (size_t k = 0; k < r->tiles_host.size() && ok; ++k) {
+        const uint32_t ty = (uint32_t)(((unsigned long long)k * magic) >> 32);
+        ok = r->tiles_host[k] == (int32_t)k && ty == (uint32_t)k / (unsigned)stx_count;
+      }
+      if (ok) r->tiles_magic = magic;
+    }
     r->tiles_px_count = 0;
     for (int b : r->tiles_host) {
       int tx = b % stx_count, ty = b / stx_count;
@@ -694,6 +705,8 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.work_counter = fc.d.p + RTRB_CNT_N + 1;
   P.status = reinterpret_cast<uint32_t*>(fc.d.p + RTRB_CNT_N + 3);
   P.extra_count = reinterpret_cast<uint32_t*>(fc.d.p + RTRB_CNT_N + 4);
+  P.hot = fc.d.p + RTRB_CNT_N + 5;
+  P.tiles_magic = (world == 1 && x0 == 0 && y0 == 0 && x1 == W && y1 == H) ? r->tiles_magic : 0u;
   P.extra_list = r->extra_list.p; P.extra_samples = r->extra_samples.p;
   // the Box code lives only in the full-counter kernel variants (rtrb_trace.cuh, trace_dispatch)
   P.count_detail = (opts.count_detail || r->n_boxes > 0) ? 1 : 0;
@@ -758,6 +771,10 @@ int finish_stats(rtrb_renderer* r, FrameCtl& fc, rtrb_stats* stats_out) {
   const uint32_t* st = reinterpret_cast<const uint32_t*>(fc.h + RTRB_CNT_N + 3);
   memset(stats_out, 0, sizeof(*stats_out));
   stats_out->rays = c[RTRB_CNT_RAYS]; stats_out->shadow_queries = c[RTRB_CNT_SHADOW];
+  for (int sl = 0; sl < RTRB_HOT_SLICES; ++sl) {
+    stats_out->rays += c[RTRB_CNT_N + 5 + 2 * sl];
+    stats_out->shadow_queries += c[RTRB_CNT_N + 5 + 2 * sl + 1];
+  }
   stats_out->highlight_hits = c[RTRB_CNT_HIGHLIGHT]; stats_out->hits = c[RTRB_CNT_HITS];
   stats_out->local_shaded = c[RTRB_CNT_LOCAL]; stats_out->lit_lights = c[RTRB_CNT_LIT];
   stats_out->mc_rays = c[RTRB_CNT_MC]; stats_out->refractions = c[RTRB_CNT_REFR];
@@ -774,7 +791,7 @@ int finish_stats(rtrb_renderer* r, FrameCtl& fc, rtrb_stats* stats_out) {
   stats_out->samples = fc.detail ? c[RTRB_CNT_SAMPLES]
                                  : (uint64_t)fc.px_count * fc.S + (uint64_t)(fc.E > 0 ? c[RTRB_CNT_ADAPTIVE] * (uint64_t)fc.E : 0);
   stats_out->status = st[0];
-  stats_out->max_stack = st[1] > 1u ? st[1] : (c[RTRB_CNT_RAYS] ? 1u : 0u);  // blocks only report depths > 1
+  stats_out->max_stack = st[1] > 1u ? st[1] : (stats_out->rays ? 1u : 0u);  // blocks only report depths > 1
   if (st[0] && c[RTRB_CNT_N] != 0ull) {  // stored complemented so that an all-zero block means "none"
     const unsigned long long key = ~c[RTRB_CNT_N];
     stats_out->first_bad_x = (int32_t)(key / (unsigned long long)fc.H);

@@ -547,11 +547,18 @@ __device__ __forceinline__ void write_pixel(const FrameParams& P, int x, int y, 
 // Decodes work item -> (tile slot k, in-tile q, x, y); returns false when the pixel is outside the window.
 __device__ __forceinline__ bool decode_pixel(const FrameParams& P, uint32_t slot, int& x, int& y) {
   uint32_t k = slot / RTRB_SUPER_PIXELS, q = slot % RTRB_SUPER_PIXELS;
-  const uint32_t tile = (uint32_t)P.tiles[k];  // tx | ty << 16
+  uint32_t tx, ty;
+  if (P.tiles_magic != 0u) {  // whole frame, one renderer: row-major tiles, no dependent load
+    ty = __umulhi(k, P.tiles_magic);
+    tx = k - ty * (uint32_t)P.stx_count;
+  } else {
+    const uint32_t tile = (uint32_t)P.tiles[k];  // tx | ty << 16
+    tx = tile & 0xffffu; ty = tile >> 16;
+  }
   int qx, qy;
   rtrb_morton_decode(q, &qx, &qy);
-  x = (int)(tile & 0xffffu) * RTRB_SUPER + qx;
-  y = (int)(tile >> 16) * RTRB_SUPER + qy;
+  x = (int)tx * RTRB_SUPER + qx;
+  y = (int)ty * RTRB_SUPER + qy;
   return x >= P.x0 && x < P.x1 && y >= P.y0 && y < P.y1;
 }
 
@@ -562,19 +569,13 @@ __device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, 
   const uint32_t rays = __reduce_add_sync(full, ctx.rays), shadow = __reduce_add_sync(full, ctx.shadow),
                  ms = __reduce_max_sync(full, ctx.max_stack);
   const int lane = threadIdx.x & 31;
-  __shared__ unsigned int blk[3];
-  if (threadIdx.x == 0) { blk[0] = 0u; blk[1] = 0u; blk[2] = 0u; }
-  __syncthreads();
   if (lane == 0) {
-    if (rays) atomicAdd(&blk[0], rays);
-    if (shadow) atomicAdd(&blk[1], shadow);
-    atomicMax(&blk[2], ms);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (blk[0]) atomicAdd(&P.counters[RTRB_CNT_RAYS], (unsigned long long)blk[0]);
-    if (blk[1]) atomicAdd(&P.counters[RTRB_CNT_SHADOW], (unsigned long long)blk[1]);
-    if (blk[2] > 1u) atomicMax(&P.status[1], blk[2]);  // 1 (just the root) is the host-side default
+    // one fire-and-forget RED per warp and counter, spread over RTRB_HOT_SLICES address pairs (the host
+    // sums the slices): no block barrier, and no single L2 line taking 65 K atomics per frame
+    unsigned long long* hot = P.hot + 2u * (((blockIdx.x << 2) | (threadIdx.x >> 5)) & (RTRB_HOT_SLICES - 1));
+    if (rays) atomicAdd(&hot[0], (unsigned long long)rays);
+    if (shadow) atomicAdd(&hot[1], (unsigned long long)shadow);
+    if (ms > 1u) atomicMax(&P.status[1], ms);  // 1 (just the root) is the host-side default
   }
   if (ctx.detail) {
 #pragma unroll

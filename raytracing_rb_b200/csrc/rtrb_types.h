@@ -134,8 +134,13 @@ struct FrameParams {
   int32_t count_detail;
   int32_t fuse_resolve;        // pre == max == 1 style frames: the trace kernel writes the pixel itself
   int32_t pixel_format;        // RTRB_FMT_*: 4 (RGBA8) or 3 (RGB8) bytes per pixel in `rgba`
-  int32_t pad_fmt;
+  // whole frame on one renderer: tile k is (k % stx_count, k / stx_count), no table load at kernel start;
+  // k / stx_count == __umulhi(k, tiles_magic), verified on the host for every k < n_tiles
+  uint32_t tiles_magic;        // 0 = use tiles[]
+  unsigned long long* hot;     // [RTRB_HOT_SLICES][2] sliced (rays, shadow queries) counters
 };
+
+#define RTRB_HOT_SLICES 64     // one atomic per warp lands on one of 64 address pairs (no L2 atomic hot spot)
 
 enum {
   RTRB_CNT_SAMPLES = 0, RTRB_CNT_RAYS, RTRB_CNT_SHADOW, RTRB_CNT_HIGHLIGHT, RTRB_CNT_HITS, RTRB_CNT_LOCAL,
