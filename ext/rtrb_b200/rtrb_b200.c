@@ -11,7 +11,8 @@
  * ruby.h); INTEGRATION.md lists the build steps for a machine with Ruby.
  *
  *   Rtrb::Renderer.new(world)                      -> bakes the scene on GPU 0 (rtrb_renderer_create)
- *   renderer.render(camera, seed = 1, precision = 1) -> String of H*W*4 RGBA8 bytes, row = y, col = x
+ *   renderer.render(camera, seed = 1, precision = 1) -> String of H*W*3 RGB8 bytes, row = y, col = x
+ *                                                     (RTRB_FMT_RGB8: alpha is always 255, camera.rb:155)
  *   renderer.stats                                 -> Hash of the last frame's counters
  */
 #include <ruby.h>
@@ -107,8 +108,21 @@ static VALUE renderer_initialize(VALUE self, VALUE world) {
       d->v_unit = NIL_P(vu) ? 1.0 : NUM2DBL(vu);
       d->has_refraction = RTEST(rr) ? 1 : 0;                                    /* plane.rb:57 */
       if (d->has_refraction) d->refractive_rate = NUM2DBL(rr);
+    } else if (is_a(o, "Alex::Objects::Box")) {
+      /* box.rb:10: the library derives the six faces exactly as Box#initialize does (box.rb:22-73) */
+      d->type = RTRB_OBJ_BOX;
+      d->texture = -1;                                                          /* Box never samples its texture */
+      vec3_into(ivar(o, "@point"), d->point, "point");
+      vec3_into(ivar(o, "@front"), d->front, "front");
+      vec3_into(ivar(o, "@up"), d->up, "up");
+      d->width_front = ivar_f(o, "@width_front", "width_front");
+      d->width_up = ivar_f(o, "@width_up", "width_up");
+      d->width_left = ivar_f(o, "@width_left", "width_left");
+      VALUE rr = ivar(o, "@refractive_rate");
+      d->has_refraction = RTEST(rr) ? 1 : 0;                                    /* plane.rb:57 on every face */
+      if (d->has_refraction) d->refractive_rate = NUM2DBL(rr);
     } else {
-      rb_raise(rb_eNotImpError, "object %ld: only Sphere and Plane run on the GPU path", i);
+      rb_raise(rb_eNotImpError, "object %ld: only Sphere, Plane and Box run on the GPU path", i);
     }
     vec3_into(ivar(o, "@diffuse_rate"), d->diffuse_rate, "diffuse_rate");
     vec3_into(ivar(o, "@reflective_attenuation"), d->reflective_attenuation, "reflective_attenuation");
@@ -179,7 +193,8 @@ static VALUE renderer_render(int argc, VALUE* argv, VALUE self) {
   c.opts.rng_mode = RTRB_RNG_CTR;
   c.opts.seed = NIL_P(seed) ? 1 : NUM2ULL(seed);                 /* main.rb:10 Random.srand(1) */
   c.opts.precision = NIL_P(precision) ? RTRB_PREC_DEFAULT : NUM2INT(precision);
-  size_t bytes = (size_t)c.cam.width * c.cam.height * 4;
+  c.opts.pixel_format = RTRB_FMT_RGB8;                           /* alpha = 255 never crosses PCIe */
+  size_t bytes = (size_t)c.cam.width * c.cam.height * 3;
   VALUE out = rb_str_new(NULL, (long)bytes);
   c.rgba = (uint8_t*)RSTRING_PTR(out);
   rb_thread_call_without_gvl(render_without_gvl, &c, RUBY_UBF_IO, NULL);
@@ -194,7 +209,7 @@ static VALUE renderer_stats(VALUE self) {
   VALUE h = rb_hash_new();
 #define PUT(k) rb_hash_aset(h, ID2SYM(rb_intern(#k)), ULL2NUM(s->last.k))
   PUT(samples); PUT(rays); PUT(shadow_queries); PUT(highlight_hits); PUT(hits); PUT(local_shaded); PUT(texel_fetches);
-  PUT(adaptive_pixels);
+  PUT(adaptive_pixels); PUT(box_tests); PUT(box_accepts);
   rb_hash_aset(h, ID2SYM(rb_intern("device_ms")), DBL2NUM(s->last.device_ms));
   rb_hash_aset(h, ID2SYM(rb_intern("status")), UINT2NUM(s->last.status));
   return h;

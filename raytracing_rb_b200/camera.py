@@ -107,6 +107,27 @@ class Camera(ConfigurableObject):
                                                          frame.stats["first_bad_y"]))
         return frame
 
+    def render_fork(self, file_path, threads, out_dir="out", seed=1, **kw):
+        """Drop-in for render_fork(file_path, threads) (camera.rb:41-68) for tooling that consumes its
+        intermediate files: ONE GPU frame, then the same `out/file_<i>.json` per column strip the forked
+        children write (camera.rb:53-65: strip i = x in [int(i/threads*W), int((i+1)/threads*W)), items in
+        x-outer / y-inner order, each {position: [x, H-1-y], color: [r, g, b]} as render_at returns them),
+        then the image as the parent does (:42-52)."""
+        import json
+        frame = self.render_frame(seed=seed, want_rgb=True, want_hit=False, **kw)
+        os.makedirs(out_dir, exist_ok=True)
+        W, H = self.width, self.height
+        for i in range(threads):
+            start_x, end_x = int(float(i) / threads * W), int(float(i + 1) / threads * W)
+            data = [{"position": [x, H - 1 - y], "color": [float(c) for c in frame.rgb[y, x]]}
+                    for x in range(start_x, end_x) for y in range(H)]
+            with open(os.path.join(out_dir, "file_%d.json" % i), "w") as f:
+                json.dump(data, f)
+        self.canvas[...] = frame.rgba
+        if file_path:
+            self.save_image(file_path)
+        return frame
+
     def render_at(self, x, y, seed=1, precision=_abi.PREC_DEFAULT):
         """camera.rb:70-99 — {position: [x, H-1-y], color: [r, g, b]} for one pixel (GPU, 1x1 window)."""
         f = self.render_frame(seed=seed, precision=precision, window=(x, y, x + 1, y + 1))

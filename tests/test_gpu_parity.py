@@ -274,3 +274,23 @@ def test_peer_push_carries_a_frame_between_renderers():
     dst.framebuffer_download(W, H * 3, out)
     assert np.array_equal(out[2 * H:], want)
     assert not out[:2 * H].any()
+
+
+def test_render_fork_json_files(tmp_path):
+    """Camera#render_fork's intermediate files (camera.rb:53-65) from one GPU frame: strip bounds, item
+    order (x outer, y inner), position = [x, H-1-y], colour = render_at's floats."""
+    import json
+    world, cam = load_scene(2, width=50, height=20)
+    frame = cam.render_fork(str(tmp_path / "img.png"), 3, out_dir=str(tmp_path / "out"))
+    items = []
+    bounds = [int(float(i) / 3 * 50) for i in range(4)]
+    for i in range(3):
+        data = json.load(open(tmp_path / "out" / ("file_%d.json" % i)))
+        assert len(data) == (bounds[i + 1] - bounds[i]) * 20
+        assert data[0]["position"] == [bounds[i], 19] and data[1]["position"] == [bounds[i], 18]
+        items += data
+    assert len(items) == 50 * 20
+    for it in items[::37]:
+        x, y = it["position"][0], 19 - it["position"][1]
+        assert it["color"] == [float(c) for c in frame.rgb[y, x]]
+    assert (tmp_path / "img.png").stat().st_size > 100
