@@ -6,7 +6,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librtrb_b200.so")
+# RTRB_B200_LIB selects another build of the same library (A/B runs of kernel variants); never a fallback
+LIB_PATH = os.environ.get("RTRB_B200_LIB") or os.path.join(_HERE, "csrc", "librtrb_b200.so")
 
 EXPORTS = (
     "rtrb_abi_version", "rtrb_last_error", "rtrb_device_count",

@@ -25,6 +25,24 @@ namespace rtrb {
 
 struct d3 { double x, y, z; };
 
+// libm's FP64 transcendentals are 100-500 SASS instructions each; inlined at every call site they push the
+// ray-tree kernels past 160 KB of code and the warps stall on instruction fetch (ncu: no_instruction is the
+// top stall of the depth-8 kernel).  One out-of-line copy each would keep more of the hot loop in the instruction
+// cache; results are unchanged (same routines).  MEASURED (round 1): out-of-line copies made configs 3-5
+// 4-5 % SLOWER (4.38 -> 4.62 ms on config 3), so the inlined form stays the default;
+// -DRTRB_OUTLINE_LIBM selects the out-of-line form.
+#ifndef RTRB_OUTLINE_LIBM
+#define RTRB_LIBM __device__ __forceinline__
+#else
+#define RTRB_LIBM static __device__ __noinline__
+#endif
+RTRB_LIBM double m_sin(double x) { return sin(x); }
+RTRB_LIBM double m_cos(double x) { return cos(x); }
+RTRB_LIBM double m_asin(double x) { return asin(x); }
+RTRB_LIBM double m_acos(double x) { return acos(x); }
+RTRB_LIBM double m_pow(double x, double y) { return pow(x, y); }
+RTRB_LIBM double m_fmod(double x, double y) { return fmod(x, y); }
+
 __device__ __forceinline__ d3 mk(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
 __device__ __forceinline__ d3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
 __device__ __forceinline__ d3 operator+(d3 a, d3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -75,10 +93,10 @@ __device__ __forceinline__ double rb_sqrt(double x, ThreadCtx& ctx) {
 }
 __device__ __forceinline__ double rb_acos(double x, ThreadCtx& ctx) {
   if (x < -1 || x > 1) ctx.status |= RTRB_ST_MATH_DOMAIN;
-  return acos(x);
+  return m_acos(x);
 }
 // Float ** exponent (world.rb:76).  pow(x, 2.0) is the correctly rounded x*x.
-__device__ __forceinline__ double rb_pow(double x, double y) { return (y == 2.0) ? x * x : pow(x, y); }
+__device__ __forceinline__ double rb_pow(double x, double y) { return (y == 2.0) ? x * x : m_pow(x, y); }
 
 // ---- counter RNG: Philox4x32-10 keyed by (seed; pixel, sample, ray path, purpose) ---------------
 __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t& c0, uint32_t& c1, uint32_t& c2,
@@ -216,7 +234,7 @@ __device__ __forceinline__ double cover_object_exact(const FrameParams& P, const
       double ct1 = fmin((r1 * r1 + dd * dd - g.radius * g.radius) / (2 * r1 * dd), 1.0);
       double ct2 = fmin((g.radius * g.radius + dd * dd - r1 * r1) / (2 * g.radius * dd), 1.0);
       double th1 = rb_acos(ct1, ctx), th2 = rb_acos(ct2, ctx);
-      double delta_s = ((th1 - sin(th1)) * r1 * r1 + (th2 - sin(th2)) * g.radius * g.radius) / 2;
+      double delta_s = ((th1 - m_sin(th1)) * r1 * r1 + (th2 - m_sin(th2)) * g.radius * g.radius) / 2;
       return factor * delta_s / s1;
     }
     RTRB_COUNT(ctx, RTRB_CNT_COV_SPH_FULL);
@@ -271,7 +289,7 @@ __device__ __forceinline__ d3 a_vertical_vector(d3 n, ThreadCtx& ctx) {
 __device__ __forceinline__ d3 texture_color(const DevMat& m, double uu, double vv, ThreadCtx& ctx) {
   double fu = (uu + m.uoff) / m.hscale, fv = (vv + m.voff) / m.vscale;
   if (!isfinite(fu) || !isfinite(fv)) { ctx.status |= RTRB_ST_NAN_TO_INT; return mk(0, 0, 0); }
-  double mu = fmod(trunc(fu), (double)m.tex_w), mv = fmod(trunc(fv), (double)m.tex_h);
+  double mu = m_fmod(trunc(fu), (double)m.tex_w), mv = m_fmod(trunc(fv), (double)m.tex_h);
   if (mu < 0) mu += m.tex_w;
   if (mv < 0) mv += m.tex_h;
   int u = (int)mu, v = (int)mv;
@@ -405,8 +423,8 @@ __device__ __forceinline__ d3 trace_sample(const FrameParams& P, d3 ro, d3 rd, u
       double sin_r = sin_i / rate;
       if (!(sin_r >= 1)) {
         if (sin_r < -1 || sin_r > 1) ctx.status |= RTRB_ST_MATH_DOMAIN;
-        double r = asin(sin_r);
-        refr_dir = nn * (-cos(r)) + normalize(refl_dir + d, ctx) * sin_r;
+        double r = m_asin(sin_r);
+        refr_dir = nn * (-m_cos(r)) + normalize(refl_dir + d, ctx) * sin_r;
         refr_org = bh.p - nn * RTRB_EPSILON;
         has_refr = true;
       }
@@ -459,7 +477,7 @@ __device__ __forceinline__ d3 trace_sample(const FrameParams& P, d3 ro, d3 rd, u
           uint32_t c0 = pixel, c1 = sample, c2 = child, c3 = 1u;
           philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
           double theta = res53(c0, c1) * RTRB_PI / 2, phi = res53(c2, c3) * RTRB_PI * 2;
-          d3 dir = nn * sin(theta) + (leftv * cos(phi) + upv * sin(phi)) * cos(theta);
+          d3 dir = nn * m_sin(theta) + (leftv * m_cos(phi) + upv * m_sin(phi)) * m_cos(theta);
           RTRB_COUNT(ctx, RTRB_CNT_MC);
           StackItem& s = stack[sp++];
           d3 a2 = att * att_pt;
@@ -512,7 +530,7 @@ __device__ __forceinline__ void lens_ray(const FrameParams& P, int x, int y, dou
   // adding a zero of either sign to `pos` gives `pos` (up to the sign of an exact zero, which no later
   // expression can observe), so the two FP64 transcendentals are skipped.
   d3 rand_vector = mk(0.0, 0.0, 0.0);
-  if (P.aperture_radius != 0.0) rand_vector = (ld3(P.left_n) * cos(theta) + upn * sin(theta)) * P.aperture_radius;
+  if (P.aperture_radius != 0.0) rand_vector = (ld3(P.left_n) * m_cos(theta) + upn * m_sin(theta)) * P.aperture_radius;
   d3 aperture = pos + rand_vector;
   d3 rf = pos - retina_position;  // ray retina -> lens centre
   double t = dot(ld3(P.focal_point) - retina_position, front) / dot(front, rf);  // intersect_plane :123-127

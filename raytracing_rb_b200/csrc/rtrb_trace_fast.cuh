@@ -708,8 +708,8 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
         const double sin_r = sin_i / rate;
         if (!(sin_r >= 1)) {
           if (sin_r < -1 || sin_r > 1) ctx.status |= RTRB_ST_MATH_DOMAIN;
-          const double rr = asin(sin_r);
-          const d3 refr_dir = nn * (-cos(rr)) + normalize(refl_dir + d, ctx) * sin_r;
+          const double rr = m_asin(sin_r);
+          const d3 refr_dir = nn * (-m_cos(rr)) + normalize(refl_dir + d, ctx) * sin_r;
           const d3 refr_org = bh.p - nn * RTRB_EPSILON;
           RTRB_COUNT(ctx, RTRB_CNT_REFR);
           StackItem& s = stack[sp++];
@@ -756,7 +756,7 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
             uint32_t c0 = pixel, c1 = sample, c2 = child, c3 = 1u;
             philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
             double theta = res53(c0, c1) * RTRB_PI / 2, phi = res53(c2, c3) * RTRB_PI * 2;
-            d3 dir = nn * sin(theta) + (leftv * cos(phi) + upv * sin(phi)) * cos(theta);
+            d3 dir = nn * m_sin(theta) + (leftv * m_cos(phi) + upv * m_sin(phi)) * m_cos(theta);
             StackItem& s = stack[sp++];
             s.ox = shade_from.x; s.oy = shade_from.y; s.oz = shade_from.z;
             s.dx = dir.x; s.dy = dir.y; s.dz = dir.z;
