@@ -172,6 +172,19 @@ def batch_cameras(world, cdoc, n, first=0):
     return cams
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPU cores NVML reports as local to GPU `index`, BEFORE any pinned host buffer
+    is allocated: on a two-socket 8-GPU box a rank whose frame buffers sit on the other socket sends every
+    device-to-host frame across the inter-socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return True
+    except Exception:
+        return False
+
+
 def run_ours(args, rank, local_rank, world_size):
     import torch
     from raytracing_rb_b200 import (Renderer, _abi, ipc_open, make_opts, measure_fma_peak, PREC_FAST64, PREC_STRICT)
@@ -180,6 +193,7 @@ def run_ours(args, rank, local_rank, world_size):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
     dist = None
     if world_size > 1:
         import torch.distributed as dist_mod

@@ -55,7 +55,11 @@ enum { RTRB_OBJ_PLANE = 0, RTRB_OBJ_SPHERE = 1, RTRB_OBJ_BOX = 2 };
 /* ---- RNG modes ----------------------------------------------------------------------------- */
 enum {
   RTRB_RNG_CTR = 0,  /* Philox4x32-10 keyed by (seed; pixel, sample, ray path, purpose); device + oracle */
-  RTRB_RNG_MT = 1    /* MT19937 genrand_res53 in the reference's consumption order; oracle only */
+  RTRB_RNG_MT = 1    /* MT19937 genrand_res53 in the reference's consumption order (Random.srand(seed), main.rb:10;
+                        one draw per lens_func, camera.rb:135, two per Monte-Carlo ray, world_object.rb:84; pixels x
+                        outer / y inner, rays LIFO).  Stream-exact VALIDATION mode: blocking calls only, one GPU,
+                        STRICT arithmetic, one thread per pixel, iterated to the fixed point of the per-pixel
+                        stream offsets (the draw counts are data dependent).  Seeds must fit 32 bits. */
 };
 
 /* ---- rtrb_render_opts.pixel_format: layout of the 8-bit frame -------------------------------- */
@@ -259,6 +263,8 @@ int rtrb_tile_partition(int width, int height, const int32_t* window_or_null, in
 /* Dependent-free FMA issue microbenchmark on `device`: the roofline denominator SURVEY.md 8d asks
  * for. which: 0 = FP32 FFMA, 1 = FP64 DFMA. Result in TFLOP/s (2 flops per FMA). */
 int rtrb_measure_fma_peak(int device, int which, double* tflops_out);
+/* Passes the last RTRB_RNG_MT frame of this renderer needed to reach its fixed point (0 if none yet). */
+int rtrb_last_mt_passes(rtrb_renderer* r);
 /* Number of kernel launches issued by this library in this process so far. */
 uint64_t rtrb_launch_count(void);
 

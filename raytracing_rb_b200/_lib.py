@@ -15,7 +15,7 @@ EXPORTS = (
     "rtrb_render_device", "rtrb_download", "rtrb_render", "rtrb_submit", "rtrb_wait",
     "rtrb_framebuffer_device_ptr", "rtrb_framebuffer_download", "rtrb_framebuffer_ipc_export", "rtrb_ipc_open", "rtrb_ipc_close",
     "rtrb_peer_push", "rtrb_peer_push_join",
-    "rtrb_render_multi", "rtrb_tile_partition", "rtrb_measure_fma_peak", "rtrb_launch_count",
+    "rtrb_render_multi", "rtrb_tile_partition", "rtrb_measure_fma_peak", "rtrb_launch_count", "rtrb_last_mt_passes",
 )
 
 _lib = None
@@ -60,6 +60,7 @@ def lib():
     L.rtrb_tile_partition.argtypes = [C.c_int, C.c_int, P(C.c_int32), C.c_int, C.c_int, P(C.c_int32), C.c_int, P(C.c_int)]
     L.rtrb_measure_fma_peak.argtypes = [C.c_int, C.c_int, P(C.c_double)]
     L.rtrb_launch_count.restype = C.c_uint64
+    L.rtrb_last_mt_passes.argtypes = [C.c_void_p]
     for name in EXPORTS:
         getattr(L, name)
     if L.rtrb_abi_version() != _abi.ABI_VERSION:

@@ -77,9 +77,9 @@ class Camera(ConfigurableObject):
 
     # -- the hot path -----------------------------------------------------------------------------
     def render_frame(self, gpus=1, seed=1, precision=_abi.PREC_DEFAULT, window=None, count_detail=False,
-                     want_rgb=True, want_hit=True):
+                     want_rgb=True, want_hit=True, rng_mode=_abi.RNG_CTR):
         """One frame on `gpus` GPUs -> Frame (see renderer.Frame)."""
-        opts = make_opts(seed=seed, precision=precision, window=window, count_detail=count_detail)
+        opts = make_opts(seed=seed, precision=precision, window=window, count_detail=count_detail, rng_mode=rng_mode)
         cam = self.camera_desc()
         if gpus <= 1:
             frame = self.renderer().render(cam, opts, want_rgb=want_rgb, want_hit=want_hit)

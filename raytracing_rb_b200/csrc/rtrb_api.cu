@@ -75,6 +75,35 @@ float4 apex_entry(const double A[3], double rho, const double C[3], double R, do
   return make_float4((float)vx, (float)vy, (float)vz, kf);
 }
 
+// MT19937 (Matsumoto & Nishimura 1998) exactly as Ruby drives it: Random.srand(seed) with a seed that fits 32
+// bits runs init_genrand(seed) (random.c rand_init), and every Random.rand is genrand_res53.  Used only by the
+// RTRB_RNG_MT validation mode: the stream is generated here and the device indexes into it.
+struct HostMT {
+  uint32_t mt[624];
+  int idx = 625;
+  void seed(uint32_t s) {
+    mt[0] = s;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    idx = 624;
+  }
+  uint32_t next32() {
+    if (idx >= 624) {
+      for (int k = 0; k < 624; ++k) {
+        uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+        mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+  }
+  double res53() {
+    const uint32_t a = next32() >> 5, b = next32() >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+  }
+};
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -160,6 +189,14 @@ struct rtrb_renderer {
   int tiles_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
   DevBuf<double> samples, extra_samples, rgb;
   DevBuf<uint32_t> extra_list;
+  // RTRB_RNG_MT validation mode
+  DevBuf<double> mt_stream;
+  DevBuf<uint32_t> mt_offset, mt_count;
+  std::vector<double> mt_host;         // the first mt_host.size() draws after init_genrand(mt_seed)
+  HostMT mt_gen;
+  uint64_t mt_seed = ~0ull;
+  size_t mt_uploaded = 0;
+  int mt_iterations = 0;               // iterations the last MT frame needed to reach its fixed point
   DevBuf<int32_t> hit;
   DevBuf<uint8_t> rgba;
   int fb_w = 0, fb_h = 0;
@@ -180,22 +217,7 @@ __device__ __forceinline__ bool slot_to_xy(const FrameParams& P, uint32_t slot, 
   return rtrb::decode_pixel(P, slot, x, y);
 }
 
-// mean of the pre samples in order, then the variance test (camera.rb:72-87)
-__device__ __forceinline__ void pre_mean(const FrameParams& P, uint32_t slot, double& ax, double& ay, double& az,
-                                         double& variance) {
-  const int S = P.pre;
-  const double* s = P.samples + (size_t)slot * S * 3;
-  ax = 0.0; ay = 0.0; az = 0.0;
-  for (int j = 0; j < S; ++j) { ax += s[j * 3 + 0]; ay += s[j * 3 + 1]; az += s[j * 3 + 2]; }
-  ax = ax / (double)S; ay = ay / (double)S; az = az / (double)S;
-  variance = 0;
-  for (int j = 0; j < S; ++j) {
-    double dx = s[j * 3 + 0] - ax, dy = s[j * 3 + 1] - ay, dz = s[j * 3 + 2] - az;
-    double m = fmax(dx, fmax(dy, dz));  // (sample - mean).to_a.max, signed
-    variance += m * m;
-  }
-  variance /= (double)S;
-}
+using rtrb::pre_mean;
 
 __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ FrameParams P) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -581,8 +603,16 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   if (cam->pre_sample_times < 1) return fail(RTRB_ERR_INVALID, "pre_sample_times must be >= 1");
   if (cam->max_sample_times < 0 || cam->monte_carlo_diffusion_times < 0 || cam->trace_depth < 0)
     return fail(RTRB_ERR_INVALID, "negative sampling parameter");
-  if (opts.rng_mode != RTRB_RNG_CTR)
-    return fail(RTRB_ERR_UNSUPPORTED, "rng_mode %d: only the counter RNG runs on the device (MT19937 is oracle-only)", opts.rng_mode);
+  if (opts.rng_mode != RTRB_RNG_CTR && opts.rng_mode != RTRB_RNG_MT) return fail(RTRB_ERR_INVALID, "unknown rng_mode %d", opts.rng_mode);
+  const bool mt_mode = opts.rng_mode == RTRB_RNG_MT;
+  if (mt_mode) {
+    // stream-exact validation mode: serial by construction (every pixel's first draw depends on how many draws
+    // all earlier pixels made), so it is blocking, single-GPU, STRICT arithmetic, and iterates to a fixed point
+    if (ctl != nullptr) return fail(RTRB_ERR_UNSUPPORTED, "RTRB_RNG_MT frames cannot be pipelined (rtrb_submit)");
+    if (opts.tile_world > 1) return fail(RTRB_ERR_UNSUPPORTED, "RTRB_RNG_MT does not combine with a tile partition");
+    if ((opts.seed >> 32) != 0) return fail(RTRB_ERR_UNSUPPORTED, "RTRB_RNG_MT: seeds above 32 bits take Ruby's init_by_array path");
+    opts.precision = RTRB_PREC_STRICT;
+  }
   if (opts.precision != RTRB_PREC_STRICT && opts.precision != RTRB_PREC_FAST64)
     return fail(RTRB_ERR_INVALID, "unknown precision mode %d", opts.precision);
   if (opts.pixel_format != RTRB_FMT_RGBA8 && opts.pixel_format != RTRB_FMT_RGB8)
@@ -728,7 +758,64 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tg.hit, n, -3);
     g_launches++;
   }
-  if (n_tiles > 0) {
+  if (n_tiles > 0 && mt_mode) {
+    // ---- RTRB_RNG_MT: offsets = exclusive prefix sums of the per-pixel draw counts, iterated until stable.
+    // The first pixel whose offset is wrong is right after the next pass (its predecessors no longer move), so
+    // the loop ends after at most one pass per pixel; in practice a handful of passes per data-dependent pixel.
+    const size_t npx = (size_t)(x1 - x0) * (size_t)(y1 - y0);
+    if (npx * (size_t)std::max(S, cam->max_sample_times) > 0x3fffffffull) return fail(RTRB_ERR_UNSUPPORTED, "window too large for RTRB_RNG_MT");
+    CUDA_TRY(r->mt_offset.ensure(npx));
+    CUDA_TRY(r->mt_count.ensure(npx));
+    std::vector<uint32_t> off(npx), cnt(npx), nxt(npx);
+    for (size_t i = 0; i < npx; ++i) off[i] = (uint32_t)(i * (size_t)S);
+    if (r->mt_seed != opts.seed) {
+      r->mt_host.clear(); r->mt_gen.seed((uint32_t)opts.seed); r->mt_seed = opts.seed; r->mt_uploaded = 0;
+    }
+    size_t want_len = npx * (size_t)(S + 1) + 4096;
+    const int max_iter = 200000;
+    int it = 0;
+    for (;; ++it) {
+      if (it >= max_iter) return fail(RTRB_ERR_UNSUPPORTED, "RTRB_RNG_MT did not reach its fixed point in %d passes", max_iter);
+      if (r->mt_host.size() < want_len) {
+        r->mt_host.reserve(want_len);
+        while (r->mt_host.size() < want_len) r->mt_host.push_back(r->mt_gen.res53());
+      }
+      if (r->mt_uploaded < r->mt_host.size()) {
+        CUDA_TRY(r->mt_stream.ensure(r->mt_host.size()));
+        CUDA_TRY(cudaMemcpyAsync(r->mt_stream.p, r->mt_host.data(), r->mt_host.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        r->mt_uploaded = r->mt_host.size();
+      }
+      P.mt_stream = r->mt_stream.p; P.mt_len = (uint32_t)std::min<size_t>(r->mt_host.size(), 0xfffffff0u);
+      P.mt_offset = r->mt_offset.p; P.mt_count = r->mt_count.p;
+      CUDA_TRY(cudaMemcpyAsync(r->mt_offset.p, off.data(), npx * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaMemsetAsync(fc.d.p, 0, RTRB_FCB_WORDS * sizeof(unsigned long long), stream));
+      if (timed) CUDA_TRY(cudaEventRecord(fc.evt0, stream));
+      CUDA_TRY(rtrb_launch_trace_mt_strict(P, stack_need, stream));
+      if (timed) CUDA_TRY(cudaEventRecord(fc.evt1, stream));
+      g_launches++;
+      CUDA_TRY(cudaMemcpyAsync(cnt.data(), r->mt_count.p, npx * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      bool overflow = false;
+      for (size_t i = 0; i < npx && !overflow; ++i) overflow = cnt[i] == 0xFFFFFFFFu;
+      if (overflow) {  // some pixel ran past the end of the stream: generate more and repeat the pass
+        want_len = r->mt_host.size() * 2;
+        if (want_len > 0xfffffff0ull) return fail(RTRB_ERR_UNSUPPORTED, "RTRB_RNG_MT stream would exceed 2^32 draws");
+        continue;
+      }
+      size_t acc = 0;
+      bool same = true;
+      for (size_t i = 0; i < npx; ++i) {
+        nxt[i] = (uint32_t)acc;
+        same = same && nxt[i] == off[i];
+        acc += cnt[i];
+      }
+      if (acc > 0xfffffff0ull) return fail(RTRB_ERR_UNSUPPORTED, "RTRB_RNG_MT stream would exceed 2^32 draws");
+      if (same) break;
+      off.swap(nxt);
+      want_len = std::max(want_len, acc + 4096);
+    }
+    r->mt_iterations = it + 1;
+  } else if (n_tiles > 0) {
     if (timed) CUDA_TRY(cudaEventRecord(fc.evt0, stream));
     CUDA_TRY(strict ? rtrb_launch_trace_pre_strict(P, stack_need, stream) : rtrb_launch_trace_pre_fast(P, stack_need, stream));
     if (timed) CUDA_TRY(cudaEventRecord(fc.evt1, stream));
@@ -868,6 +955,7 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   if (!r) return RTRB_OK;
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
+  r->mt_stream.release(); r->mt_offset.release(); r->mt_count.release();
   r->geom.release(); r->mat.release(); r->lights.release(); r->lens_tab.release(); r->boxes.release();
   r->bvh.release(); r->light_tab.release();
   r->cull_sph.release(); r->cull_pl.release(); r->sph_index.release(); r->pl_index.release(); r->lights_f.release(); r->tiles.release(); r->samples.release();
@@ -1155,6 +1243,8 @@ int rtrb_tile_partition(int width, int height, const int32_t* window, int tile_r
     for (int i = 0; i < (int)t.size() && i < capacity; ++i) tiles_out[i] = t[i];
   return RTRB_OK;
 }
+
+int rtrb_last_mt_passes(rtrb_renderer* r) { return r ? r->mt_iterations : 0; }
 
 int rtrb_measure_fma_peak(int device, int which, double* tflops_out) {
   if (!tflops_out) return fail(RTRB_ERR_INVALID, "tflops_out is NULL");

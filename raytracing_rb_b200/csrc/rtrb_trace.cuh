@@ -297,6 +297,20 @@ __device__ __forceinline__ d3 texture_color(const DevMat& m, double uu, double v
   return mk(__ldg(p) / 256.0, __ldg(p + 1) / 256.0, __ldg(p + 2) / 256.0);
 }
 
+// RTRB_RNG_MT: a thread's position in the host-generated MT19937 stream (Random.rand, camera.rb:135 and
+// world_object.rb:84, consumed in program order).
+struct MtCursor {
+  const double* s;
+  uint32_t pos, len;
+  bool overflow;
+  __device__ __forceinline__ double next() {
+    double v = 0.0;
+    if (pos < len) v = s[pos]; else overflow = true;
+    pos++;
+    return v;
+  }
+};
+
 struct StackItem {
   double ox, oy, oz, dx, dy, dz, ax, ay, az;
   int32_t depth;
@@ -305,9 +319,9 @@ struct StackItem {
 
 // RayTracer#trace_sync for one sample.  Returns the summed colour; *primary_hit gets the root ray's
 // World#intersect winner (-1 miss, -2 highlight-terminated).
-template <int MAXS>
+template <int MAXS, bool MT = false>
 __device__ __forceinline__ d3 trace_sample(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
-                                           ThreadCtx& ctx, int* primary_hit) {
+                                           ThreadCtx& ctx, int* primary_hit, MtCursor* mt = nullptr) {
   StackItem stack[MAXS];
   int sp = 0;
   stack[0].ox = ro.x; stack[0].oy = ro.y; stack[0].oz = ro.z;
@@ -474,9 +488,15 @@ __device__ __forceinline__ d3 trace_sample(const FrameParams& P, d3 ro, d3 rd, u
         d3 upv = cross(nn, leftv);
         for (int m = 0; m < P.mc; ++m) {
           uint32_t child = it.path * K + (uint32_t)(2 + m);
-          uint32_t c0 = pixel, c1 = sample, c2 = child, c3 = 1u;
-          philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
-          double theta = res53(c0, c1) * RTRB_PI / 2, phi = res53(c2, c3) * RTRB_PI * 2;
+          double u_theta, u_phi;  // theta's draw first (world_object.rb:84)
+          if constexpr (MT) {
+            u_theta = mt->next(); u_phi = mt->next();
+          } else {
+            uint32_t c0 = pixel, c1 = sample, c2 = child, c3 = 1u;
+            philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
+            u_theta = res53(c0, c1); u_phi = res53(c2, c3);
+          }
+          double theta = u_theta * RTRB_PI / 2, phi = u_phi * RTRB_PI * 2;
           d3 dir = nn * m_sin(theta) + (leftv * m_cos(phi) + upv * m_sin(phi)) * m_cos(theta);
           RTRB_COUNT(ctx, RTRB_CNT_MC);
           StackItem& s = stack[sp++];
@@ -707,6 +727,77 @@ __device__ __forceinline__ void trace_extra_body(const FrameParams& P) {
     out[0] = col.x; out[1] = col.y; out[2] = col.z;
   }
   flush_ctx(P, ctx, x, y, any);
+}
+
+// mean of the pre samples in order, then the variance test (camera.rb:72-87)
+__device__ __forceinline__ void pre_mean(const FrameParams& P, uint32_t slot, double& ax, double& ay, double& az,
+                                         double& variance) {
+  const int S = P.pre;
+  const double* s = P.samples + (size_t)slot * S * 3;
+  ax = 0.0; ay = 0.0; az = 0.0;
+  for (int j = 0; j < S; ++j) { ax += s[j * 3 + 0]; ay += s[j * 3 + 1]; az += s[j * 3 + 2]; }
+  ax = ax / (double)S; ay = ay / (double)S; az = az / (double)S;
+  variance = 0;
+  for (int j = 0; j < S; ++j) {
+    double dx = s[j * 3 + 0] - ax, dy = s[j * 3 + 1] - ay, dz = s[j * 3 + 2] - az;
+    double m = fmax(dx, fmax(dy, dz));  // (sample - mean).to_a.max, signed
+    variance += m * m;
+  }
+  variance /= (double)S;
+}
+
+// RTRB_RNG_MT: Camera#render_at (camera.rb:70-99) for ONE pixel in ONE thread, because the reference's
+// MT19937 draws are consumed in program order: every sample's lens draw (camera.rb:135, drawn even when the
+// aperture is 0), its Monte-Carlo draws in LIFO ray order, then the next sample, then the adaptive samples.
+// The thread reads its draws from mt_stream starting at mt_offset[pixel order] and reports how many it used;
+// the host iterates offsets = prefix sums of the counts until they stop changing (rtrb_api.cu).
+template <int MAXS, bool DETAIL>
+__device__ __forceinline__ void trace_mt_body(const FrameParams& P) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  ThreadCtx ctx;
+  init_ctx(ctx, DETAIL);
+  int x = 0, y = 0;
+  bool active = false;
+  if (slot < (uint32_t)P.n_tiles * RTRB_SUPER_PIXELS) active = decode_pixel(P, slot, x, y);
+  if (active) {
+    const uint32_t pixel = (uint32_t)y * (uint32_t)P.width + (uint32_t)x;
+    const uint32_t order = (uint32_t)(x - P.x0) * (uint32_t)(P.y1 - P.y0) + (uint32_t)(y - P.y0);
+    MtCursor cur;
+    cur.s = P.mt_stream; cur.pos = P.mt_offset[order]; cur.len = P.mt_len; cur.overflow = false;
+    const uint32_t start = cur.pos;
+    const int S = P.pre;
+    double* smp = P.samples + (size_t)slot * S * 3;
+    for (int j = 0; j < S; ++j) {
+      const double theta = cur.next();
+      d3 ro, rd;
+      lens_ray(P, x, y, theta, ro, rd);
+      int ph;
+      d3 col = trace_sample<MAXS, true>(P, ro, rd, pixel, (uint32_t)j, ctx, &ph, &cur);
+      RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
+      smp[j * 3 + 0] = col.x; smp[j * 3 + 1] = col.y; smp[j * 3 + 2] = col.z;
+      if (j == 0 && P.hit) P.hit[(size_t)y * P.width + x] = ph;
+    }
+    double ax, ay, az, variance;
+    pre_mean(P, slot, ax, ay, az, variance);
+    if (variance >= P.variant_threshold) {
+      atomicAdd(&P.counters[RTRB_CNT_ADAPTIVE], 1ull);
+      double cx = 0.0, cy = 0.0, cz = 0.0;
+      for (int j = S; j < P.max_samples; ++j) {
+        const double theta = cur.next();
+        d3 ro, rd;
+        lens_ray(P, x, y, theta, ro, rd);
+        int ph;
+        d3 col = trace_sample<MAXS, true>(P, ro, rd, pixel, (uint32_t)j, ctx, &ph, &cur);
+        RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
+        cx += col.x; cy += col.y; cz += col.z;
+      }
+      const double fp = (double)S, fm = (double)P.max_samples;
+      ax = (ax * fp + cx) / fm; ay = (ay * fp + cy) / fm; az = (az * fp + cz) / fm;  // camera.rb:93
+    }
+    write_pixel(P, x, y, ax, ay, az);
+    P.mt_count[order] = cur.overflow ? 0xFFFFFFFFu : cur.pos - start;
+  }
+  flush_ctx(P, ctx, x, y, active);
 }
 
 }  // namespace rtrb

@@ -17,6 +17,20 @@ __global__ void __launch_bounds__(kBlock) trace_extra_strict_kernel(const __grid
 }
 
 template <int MAXS, bool DETAIL>
+__global__ void __launch_bounds__(kBlock) trace_mt_strict_kernel(const __grid_constant__ FrameParams P) {
+  rtrb::trace_mt_body<MAXS, DETAIL>(P);
+}
+template <int MAXS, bool DETAIL>
+cudaError_t launch_mt(const FrameParams& P, cudaStream_t s) {
+  unsigned long long total = (unsigned long long)P.n_tiles * RTRB_SUPER_PIXELS;  // one thread per PIXEL
+  if (total == 0) return cudaSuccess;
+  unsigned long long blocks = (total + kBlock - 1) / kBlock;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  trace_mt_strict_kernel<MAXS, DETAIL><<<(unsigned)blocks, kBlock, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+template <int MAXS, bool DETAIL>
 cudaError_t launch_pre(const FrameParams& P, cudaStream_t s) {
   unsigned long long total = (unsigned long long)P.n_tiles * RTRB_SUPER_PIXELS * (unsigned long long)P.pre;
   if (total == 0) return cudaSuccess;
@@ -51,4 +65,7 @@ cudaError_t rtrb_launch_trace_pre_strict(const FrameParams& P, int stack_need, c
 }
 cudaError_t rtrb_launch_trace_extra_strict(const FrameParams& P, int stack_need, cudaStream_t s) {
   RTRB_DISPATCH(launch_extra, P, stack_need, s);
+}
+cudaError_t rtrb_launch_trace_mt_strict(const FrameParams& P, int stack_need, cudaStream_t s) {
+  RTRB_DISPATCH(launch_mt, P, stack_need, s);
 }

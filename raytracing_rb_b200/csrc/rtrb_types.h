@@ -138,6 +138,12 @@ struct FrameParams {
   // k / stx_count == __umulhi(k, tiles_magic), verified on the host for every k < n_tiles
   uint32_t tiles_magic;        // 0 = use tiles[]
   unsigned long long* hot;     // [RTRB_HOT_SLICES][2] sliced (rays, shadow queries) counters
+  // RTRB_RNG_MT (stream-exact validation mode): the reference's MT19937 doubles, generated on the host, and
+  // for every pixel of the window in the reference's order (x outer, y inner) where its draws start
+  const double* mt_stream;     // [mt_len] genrand_res53 values after init_genrand(seed)
+  const uint32_t* mt_offset;   // [window pixels] first draw of pixel (x - x0) * (y1 - y0) + (y - y0)
+  uint32_t* mt_count;          // [window pixels] out: draws the pixel consumed (0xFFFFFFFF = ran past mt_len)
+  uint32_t mt_len, pad_mt;
 };
 
 #define RTRB_HOT_SLICES 64     // one atomic per warp lands on one of 64 address pairs (no L2 atomic hot spot)

@@ -114,6 +114,10 @@ class Renderer:
     def peer_push_join(self, stream=None):
         check(lib().rtrb_peer_push_join(self._h, C.c_void_p(stream) if stream else None))
 
+    def last_mt_passes(self):
+        """Passes the last RNG_MT frame needed to reach the fixed point of its stream offsets."""
+        return int(lib().rtrb_last_mt_passes(self._h))
+
     def framebuffer_ptr(self, width, height):
         p = C.c_void_p()
         check(lib().rtrb_framebuffer_device_ptr(self._h, width, height, C.byref(p)))

@@ -148,8 +148,10 @@ def test_device_rejects_what_it_cannot_do(oracle_mod):
     from raytracing_rb_b200 import _abi
     from raytracing_rb_b200._lib import RtrbError
     world, cam = load_scene(1)
+    with pytest.raises(RtrbError):  # MT stream mode is serial by construction: no tile partition, 32-bit seeds
+        cam.renderer().render(cam.camera_desc(), make_opts(rng_mode=_abi.RNG_MT, tile_rank=0, tile_world=2))
     with pytest.raises(RtrbError):
-        cam.renderer().render(cam.camera_desc(), make_opts(rng_mode=_abi.RNG_MT))
+        cam.renderer().render(cam.camera_desc(), make_opts(rng_mode=_abi.RNG_MT, seed=1 << 40))
     c = cam.camera_desc()
     c.trace_depth = 100
     c.monte_carlo_diffusion_times = 4
@@ -294,3 +296,31 @@ def test_render_fork_json_files(tmp_path):
         x, y = it["position"][0], 19 - it["position"][1]
         assert it["color"] == [float(c) for c in frame.rgb[y, x]]
     assert (tmp_path / "img.png").stat().st_size > 100
+
+
+@pytest.mark.parametrize("config_id,kw,window", [
+    (1, {}, None),                                   # default scene: adaptive 3..10 samples + Monte-Carlo rays
+    (4, dict(width=96, height=54), None),            # 16 spp, MC rays in every shadow
+    (3, dict(width=160, height=90), (40, 0, 80, 90)),  # a render_fork column strip: the stream restarts at its first pixel
+])
+def test_mt19937_stream_mode_matches_oracle(oracle_mod, config_id, kw, window):
+    """RTRB_RNG_MT on the device - the reference's own random stream (Random.srand(1),
+    main.rb:10) consumed in its own order.  Same stream, same order => the frame must equal the oracle's MT
+    frame, including which pixels take the adaptive branch and every ray counter."""
+    from raytracing_rb_b200 import RNG_MT
+    world, cam = load_scene(config_id, **kw)
+    opts = make_opts(seed=1, rng_mode=RNG_MT, window=window)
+    ref = oracle_mod.OracleScene(world.to_scene_desc()).render(cam.camera_desc(), opts, threads=1)
+    got = cam.render_frame(seed=1, rng_mode=RNG_MT, window=window, count_detail=True)
+    print("MT fixed point after %d passes" % cam.renderer().last_mt_passes())
+    if window:  # compare the strip only: pixels outside it are not rendered by either side
+        x0, y0, x1, y1 = window
+        for f in (ref, got):
+            f.rgba, f.rgb, f.hit = f.rgba[y0:y1, x0:x1], f.rgb[y0:y1, x0:x1], f.hit[y0:y1, x0:x1]
+    check(ref, got, True)
+    assert got.stats["adaptive_pixels"] == ref.stats["adaptive_pixels"]
+    assert got.stats["mc_rays"] == ref.stats["mc_rays"]
+    ctr = cam.render_frame(seed=1, window=window)
+    if window:
+        ctr.rgb = ctr.rgb[y0:y1, x0:x1]
+    assert not np.array_equal(ctr.rgb, got.rgb)  # a different stream than the counter RNG
