@@ -149,8 +149,8 @@ def run_reference(args, rank, world_size):
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name + "; one step = a batch of %d frames (camera dolly)" % args.frames_per_step,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name + "; one step = a batch of %d frames per GPU (camera dolly)" % args.frames_per_step,
                    "frames_per_step": args.frames_per_step, "host": "CPU only (one frame of the batch per step)",
                    "ruby_present": ruby},
         "frames_per_s_equiv": args.steps / dt * (ww / W),
@@ -193,7 +193,8 @@ def run_ours(args, rank, local_rank, world_size):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    bind_to_gpu_numa_node(local_rank)
+    if world_size > 1:  # (N = 1 keeps every host core: the CPU baseline leg runs in this process)
+        bind_to_gpu_numa_node(local_rank)
     dist = None
     if world_size > 1:
         import torch.distributed as dist_mod
