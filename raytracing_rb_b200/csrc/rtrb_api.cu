@@ -173,6 +173,17 @@ struct rtrb_renderer {
   DevBuf<float4> cull_sph, cull_pl;
   DevBuf<BvhNode> bvh;
   DevBuf<float4> light_tab;            // apex tables of the lights (linear-filter scenes)
+  // small scenes: host copy of the per-ray tables that travel in the kernel parameters (FrameParams::k_*)
+  struct SmallTables {
+    float4 light_tab[RTRB_K_LIGHTS][RTRB_APEX_MAX];
+    float4 cull_sph[RTRB_APEX_MAX];
+    float4 cull_pl[2 * RTRB_K_PLANES];
+    DevLight lights[RTRB_K_LIGHTS];
+    DevLightF lights_f[RTRB_K_LIGHTS];
+    int32_t pl_index[RTRB_K_PLANES];
+    int32_t has_light_tab;
+  } k;
+  bool small_scene = false;            // <= 32 spheres/boxes, <= 8 planes, <= 2 lights: linear-filter kernels
   std::vector<double> sph_world;       // (cx, cy, cz, R) in cull_sph[] order, FP64, for the per-frame camera table
   DevBuf<int32_t> sph_index, pl_index;
   DevBuf<DevLightF> lights_f;
@@ -470,7 +481,8 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
   }
   // the BVH build reorders the spheres so that every leaf is a contiguous run of cull_sph[]
   std::vector<BvhNode> nodes;
-  if ((int)bsph.size() > RTRB_BVH_MIN_SPHERES) nodes = rtrb_bvh::build_tree(bsph);
+  r->small_scene = (int)bsph.size() <= RTRB_BVH_MIN_SPHERES && (int)ipl.size() <= RTRB_K_PLANES && s->n_lights <= RTRB_K_LIGHTS;
+  if (!r->small_scene) nodes = rtrb_bvh::build_tree(bsph);
   for (const BvhBuildSphere& bs : bsph) {
     float w = (float)bs.r;
     if (bs.bound_only) {  // rounded up, sign bit set
@@ -487,7 +499,8 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
   r->n_sph = (int)isph.size(); r->n_pl = (int)ipl.size();
   r->sph_world.clear();
   for (const BvhBuildSphere& bs : bsph) { for (int k = 0; k < 3; ++k) r->sph_world.push_back(bs.c[k]); r->sph_world.push_back(bs.r); }
-  if (nodes.empty() && !bsph.empty() && (int)bsph.size() <= RTRB_APEX_MAX && s->n_lights > 0) {
+  memset(&r->k, 0, sizeof(r->k));
+  if (r->small_scene && !bsph.empty() && s->n_lights > 0) {
     std::vector<float4> lt((size_t)s->n_lights * bsph.size());
     for (int l = 0; l < s->n_lights; ++l) {
       double lm = fmax(fabs(s->lights[l].position[0]), fmax(fabs(s->lights[l].position[1]), fabs(s->lights[l].position[2])));
@@ -496,6 +509,11 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
     }
     CUDA_TRY(r->light_tab.ensure(lt.size()));
     CUDA_TRY(cudaMemcpy(r->light_tab.p, lt.data(), lt.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    for (int l = 0; l < RTRB_K_LIGHTS; ++l)
+      for (int k = 0; k < RTRB_APEX_MAX; ++k)
+        r->k.light_tab[l][k] = (l < s->n_lights && k < (int)bsph.size()) ? lt[(size_t)l * bsph.size() + k]
+                                                                        : make_float4(0.0f, 0.0f, 0.0f, INFINITY);
+    r->k.has_light_tab = 1;
   }
   r->m_scene = m_scene;
   r->max_distance_f = nextafterf((float)s->max_distance, INFINITY);
@@ -508,6 +526,12 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
     lf[i].mode = (thr > 1e-4 && thr < 1.5) ? 1 : 0;
     double c = cos(thr);
     lf[i].cos2_thr = (float)(c * c);
+  }
+  if (r->small_scene) {
+    for (size_t k = 0; k < csph.size(); ++k) r->k.cull_sph[k] = csph[k];
+    for (size_t k = 0; k < cpl.size(); ++k) r->k.cull_pl[k] = cpl[k];
+    for (size_t k = 0; k < ipl.size(); ++k) r->k.pl_index[k] = ipl[k];
+    for (int l = 0; l < s->n_lights; ++l) { r->k.lights[l] = lights[l]; r->k.lights_f[l] = lf[l]; }
   }
   CUDA_TRY(r->cull_sph.ensure(std::max<size_t>(1, csph.size())));
   CUDA_TRY(r->sph_index.ensure(std::max<size_t>(1, isph.size())));
@@ -715,7 +739,17 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.cull_sph = r->cull_sph.p; P.sph_index = r->sph_index.p; P.cull_pl = r->cull_pl.p; P.pl_index = r->pl_index.p;
   P.lights_f = r->lights_f.p; P.n_sph = r->n_sph; P.n_pl = r->n_pl; P.bvh = r->bvh.p;
   P.m_scene = r->m_scene; P.max_distance_f = r->max_distance_f;
-  P.use_bvh = r->n_sph > RTRB_BVH_MIN_SPHERES ? 1 : 0;
+  P.use_bvh = r->small_scene ? 0 : 1;
+  if (r->small_scene) {
+    static_assert(sizeof(r->k.light_tab) == sizeof(P.k_light_tab) && sizeof(r->k.lights) == sizeof(P.k_lights), "table layout");
+    memcpy(P.k_light_tab, r->k.light_tab, sizeof(P.k_light_tab));
+    memcpy(P.k_cull_sph, r->k.cull_sph, sizeof(P.k_cull_sph));
+    memcpy(P.k_cull_pl, r->k.cull_pl, sizeof(P.k_cull_pl));
+    memcpy(P.k_lights, r->k.lights, sizeof(P.k_lights));
+    memcpy(P.k_lights_f, r->k.lights_f, sizeof(P.k_lights_f));
+    memcpy(P.k_pl_index, r->k.pl_index, sizeof(P.k_pl_index));
+    P.k_has_light_tab = r->k.has_light_tab;
+  }
   P.light_tab = r->light_tab.p;  // nullptr unless the scene uses the linear filter
   P.cam_tab_valid = 0;
   if (!P.use_bvh && r->n_sph > 0 && r->n_sph <= RTRB_APEX_MAX) {

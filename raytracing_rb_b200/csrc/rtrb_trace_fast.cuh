@@ -390,14 +390,26 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
 }
 
 // ---- SMALL SCENES: linear FP32 scan, no tree (cull_sph[] stays in world_objects order) -------------
+// KT = "constant tables": the depth-1 kernels read the uniformly indexed per-ray tables (plane filter records,
+// light apex tables, lights) from the kernel-parameter constant bank (FrameParams::k_*); measured -4 % on config 2.
+// The ray-tree kernels (MAXS > 1) keep them in global memory: there the extra 2 KB of constants evict the
+// camera table and the FP64 literals from the small constant cache, measured +3 % on configs 3/4.
+template <bool KT> __device__ __forceinline__ float4 pl_rec(const FrameParams& P, int j) {
+  if constexpr (KT) return P.k_cull_pl[j]; else return __ldg(&P.cull_pl[j]);
+}
+template <bool KT> __device__ __forceinline__ int pl_world_index(const FrameParams& P, int k) {
+  if constexpr (KT) return P.k_pl_index[k]; else return P.pl_index[k];
+}
 // World#intersect (world.rb:37-59) = FP32 filter over every object + exact test of the survivors.
 // Survivors of the linear filter are a 32-bit mask over cull_sph[] (n_sph <= RTRB_APEX_MAX = 32 here),
 // bit k = sphere k in world_objects order; the hot loop is branch-free.
+template <bool KT>
 __device__ __forceinline__ uint32_t line_survivors_generic(const FrameParams& P, const CullRay& r) {
   uint32_t m = 0u;
 #pragma unroll 4
   for (int k = 0; k < P.n_sph; ++k) {
-    const float4 s = __ldg(&P.cull_sph[k]);
+    float4 s;
+    if constexpr (KT) s = P.k_cull_sph[k]; else s = __ldg(&P.cull_sph[k]);
     m |= (sphere_line_misses(s, r) ? 0u : 1u) << k;
   }
   return m;
@@ -419,20 +431,32 @@ __device__ __forceinline__ uint32_t line_survivors_camera(const FrameParams& P, 
   }
   return m;
 }
+template <bool KT>
 __device__ __forceinline__ uint32_t line_survivors_light(const FrameParams& P, const int light_index, const CullRay& r) {
-  const float4* tab = P.light_tab + (size_t)light_index * P.n_sph;
   uint32_t m = 0u;
+  if constexpr (!KT) {
+    const float4* tab = P.light_tab + (size_t)light_index * P.n_sph;
 #pragma unroll 4
-  for (int k = 0; k < P.n_sph; ++k) m |= apex_test(__ldg(&tab[k]), r) << k;
+    for (int k = 0; k < P.n_sph; ++k) m |= apex_test(__ldg(&tab[k]), r) << k;
+    return m;
+  }
+  // constant-bank table, eight spheres per uniform branch like the camera table
+#pragma unroll
+  for (int blk = 0; blk < RTRB_APEX_MAX / 8; ++blk) {
+    if (blk * 8 < P.n_sph) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m |= apex_test(P.k_light_tab[light_index][blk * 8 + j], r) << (blk * 8 + j);
+    }
+  }
   return m;
 }
 
 // World#intersect (world.rb:37-59) = FP32 filter over every object + exact test of the survivors.
-template <bool BOX>
+template <bool BOX, bool KT>
 __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx, const bool through_lens) {
-  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > 8) return closest_hit_scan<BOX>(P, o, d, bh, ctx);
-  const uint32_t mask = (through_lens && P.cam_tab_valid) ? line_survivors_camera(P, r) : line_survivors_generic(P, r);
+  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > RTRB_K_PLANES) return closest_hit_scan<BOX>(P, o, d, bh, ctx);
+  const uint32_t mask = (through_lens && P.cam_tab_valid) ? line_survivors_camera(P, r) : line_survivors_generic<KT>(P, r);
   // pass 1 (only when something can be pruned): the smallest certain upper bound; nothing at or beyond
   // max_distance can win (world.rb:39)
   float best_hi = P.max_distance_f;
@@ -443,7 +467,7 @@ __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3
     }
     for (int k = 0; k < P.n_pl; ++k) {
       float lo, hi;
-      if (classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
+      if (classify_plane(pl_rec<KT>(P, 2 * k), pl_rec<KT>(P, 2 * k + 1), r, lo, hi) == 2) best_hi = fminf(best_hi, hi);
     }
   }
   // pass 2: exact FP64 evaluation of whatever can still win; (distance, index) lexicographic order
@@ -470,9 +494,9 @@ __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3
   }
   for (int k = 0; k < P.n_pl; ++k) {
     float lo, hi;
-    const int kind = classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi);
+    const int kind = classify_plane(pl_rec<KT>(P, 2 * k), pl_rec<KT>(P, 2 * k + 1), r, lo, hi);
     if (kind == 0 || !(lo <= best_hi)) continue;
-    const int i = P.pl_index[k];
+    const int i = pl_world_index<KT>(P, k);
     const DevGeom g = P.geom[i];
     HitRec h;
     double den;
@@ -489,7 +513,7 @@ __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3
 // An object the probe ray certainly misses (or certainly meets beyond the light) has factor 0, hence
 // cover exactly 0 (sphere.rb:29,45-53 multiply everything by factor; world_object.rb:43-47), and
 // total - 0 == total, so skipping it leaves the running difference bit-identical.
-template <bool BOX>
+template <bool BOX, bool KT>
 __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 target, const DevLight& L, const int light_index,
                                                   ThreadCtx& ctx) {
   CoverRay c;
@@ -504,13 +528,13 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
     const float lx = (float)c.lt.x, ly = (float)c.lt.y, lz = (float)c.lt.z;
     far = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) * 1.00001f + 2.0f * r.E;
   }
-  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > 32) return lit_area<BOX>(P, target, L, ctx);
+  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > RTRB_K_PLANES) return lit_area<BOX>(P, target, L, ctx);
   // the probe ray's line passes through the light: apex table of this light when there is one
-  uint32_t sm = (P.light_tab != nullptr) ? line_survivors_light(P, light_index, r) : line_survivors_generic(P, r);
+  uint32_t sm = (P.k_has_light_tab != 0) ? line_survivors_light<KT>(P, light_index, r) : line_survivors_generic<KT>(P, r);
   uint32_t qm = 0u;
   for (int k = 0; k < P.n_pl; ++k) {
     float lo, hi;
-    const int kind = classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi);
+    const int kind = classify_plane(pl_rec<KT>(P, 2 * k), pl_rec<KT>(P, 2 * k + 1), r, lo, hi);
     if (kind != 0 && !(lo > far)) qm |= 1u << k;
   }
   double total = 1;
@@ -519,7 +543,7 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
   while (sm != 0u || qm != 0u) {
     const int ks = sm ? __ffs(sm) - 1 : -1, kq = qm ? __ffs(qm) - 1 : -1;
     const int is = ks >= 0 ? P.sph_index[ks] : 0x7fffffff;
-    const int iq = kq >= 0 ? P.pl_index[kq] : 0x7fffffff;
+    const int iq = kq >= 0 ? pl_world_index<KT>(P, kq) : 0x7fffffff;
     if (is < iq) {
       sm &= sm - 1u;
       float lo, hi;
@@ -541,19 +565,32 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
   return fmax(total, 0.0);
 }
 
+// Only UNIFORMLY indexed tables are read from the constant bank (every lane the same element: the apex-table
+// and plane loops, the lights).  Survivor lookups (cull_sph[k], sph_index[k] with a per-lane k) stay in global
+// memory: divergent constant loads serialise, measured +3.7 % on the depth-8 kernels.
+// Lights: constant-bank copies in the KT kernels (<= RTRB_K_LIGHTS lights), global memory otherwise.
+template <bool KT>
+__device__ __forceinline__ const DevLight& light_at(const FrameParams& P, int l) {
+  if constexpr (KT) return P.k_lights[l]; else return P.lights[l];
+}
+template <bool KT>
+__device__ __forceinline__ const DevLightF& light_f_at(const FrameParams& P, int l) {
+  if constexpr (KT) return P.k_lights_f[l]; else return P.lights_f[l];
+}
+
 // Compile-time choice: kernels are instantiated once per filter so each stays compact (the linear
 // scan wins below ~32 spheres: measured 5.56 vs 6.05 ms on config 3; the BVH wins 5x on config 5).
-template <bool BVH, bool BOX>
+template <bool BVH, bool BOX, bool KT>
 __device__ __forceinline__ int closest_hit_fast(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx, const bool through_lens) {
   if constexpr (BVH) return closest_hit_bvh<BOX>(P, o, d, r, bh, ctx);
-  else return closest_hit_linear<BOX>(P, o, d, r, bh, ctx, through_lens);
+  else return closest_hit_linear<BOX, KT>(P, o, d, r, bh, ctx, through_lens);
 }
-template <bool BVH, bool BOX>
+template <bool BVH, bool BOX, bool KT>
 __device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target, const DevLight& L, const int light_index,
                                                 ThreadCtx& ctx) {
   if constexpr (BVH) return lit_area_bvh<BOX>(P, target, L, ctx);
-  else return lit_area_linear<BOX>(P, target, L, light_index, ctx);
+  else return lit_area_linear<BOX, KT>(P, target, L, light_index, ctx);
 }
 
 // World#high_lights match for one light (world.rb:86-93): acos(|cos|) < threshold, filtered in FP32 on
@@ -594,6 +631,7 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
                                                   d3& sum, ThreadCtx& ctx, uint32_t pixel, uint32_t sample,
                                                   bool is_first, int* primary_hit) {
   const uint32_t K = (uint32_t)(P.mc + 2);
+  constexpr bool KT = !BVH && MAXS == 1;  // constant-bank tables: depth-1 linear-filter kernels only (see pl_rec)
   {
     const d3 o = mk(it.ox, it.oy, it.oz), d = mk(it.dx, it.dy, it.dz), att = mk(it.ax, it.ay, it.az);
     if (it.depth <= 0 || attenuation_dead(att)) return;  // rt_map :52
@@ -606,11 +644,11 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
       unsigned long long hl_mask = 0ull;
       int hl_n = 0;
       for (int l = 0; l < P.n_lights; ++l)
-        if (highlight_match_fast(P.lights[l], P.lights_f[l], o, d, r, ctx)) { hl_mask |= 1ull << l; hl_n++; }
+        if (highlight_match_fast(light_at<KT>(P, l), light_f_at<KT>(P, l), o, d, r, ctx)) { hl_mask |= 1ull << l; hl_n++; }
       if (hl_n > 0) {
         for (int l = 0; l < P.n_lights; ++l) {
           if (!((hl_mask >> l) & 1ull)) return;
-          d3 c = att * ld3(P.lights[l].color_hl);
+          d3 c = att * ld3(light_at<KT>(P, l).color_hl);
           if (hl_n != 1) c = c / (double)hl_n;  // x / 1.0 == x
           sum = sum + c;
           if (sum.x > 1 || sum.y > 1 || sum.z > 1) ctx.status |= RTRB_ST_COLOR_GT_1;
@@ -624,7 +662,7 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
     // ---- World#intersect ----
     HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false;
     if constexpr (BOX) bh.face = 0;
-    const int best_i = closest_hit_fast<BVH, BOX>(P, o, d, r, bh, ctx, is_first);
+    const int best_i = closest_hit_fast<BVH, BOX, KT>(P, o, d, r, bh, ctx, is_first);
     if (best_i < 0) return;
     if (is_first) *primary_hit = best_i;
     RTRB_COUNT(ctx, RTRB_CNT_HITS);
@@ -726,9 +764,9 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
     d3 contrib = mk(0.0, 0.0, 0.0);
     int n_lit = 0;
     for (int l = 0; l < P.n_lights; ++l) {
-      const DevLight& L = P.lights[l];
+      const DevLight& L = light_at<KT>(P, l);
       ctx.shadow++;
-      const double area = lit_area_fast<BVH, BOX>(P, shade_from, L, l, ctx);
+      const double area = lit_area_fast<BVH, BOX, KT>(P, shade_from, L, l, ctx);
       if (area > 0) {
         double w = rb_pow(area, P.soft_shadow_exponent);
         if (P.n_lights != 1) w = w / (double)P.n_lights;  // x / 1.0 == x

@@ -16,6 +16,8 @@
 #define RTRB_SUPER 32                 // super-tile edge in pixels (tile partition unit across GPUs)
 #define RTRB_SUPER_PIXELS (RTRB_SUPER * RTRB_SUPER)
 #define RTRB_APEX_MAX 32              // linear-filter scenes (<= 32 spheres) get apex tables, see FrameParams
+#define RTRB_K_PLANES 8               // ... have at most this many planes
+#define RTRB_K_LIGHTS 2               // ... and at most this many lights (anything larger runs the BVH kernels)
 
 struct DevGeom {      // 64 B
   double px, py, pz;  // sphere centre / plane point
@@ -144,6 +146,17 @@ struct FrameParams {
   const uint32_t* mt_offset;   // [window pixels] first draw of pixel (x - x0) * (y1 - y0) + (y - y0)
   uint32_t* mt_count;          // [window pixels] out: draws the pixel consumed (0xFFFFFFFF = ran past mt_len)
   uint32_t mt_len, pad_mt;
+  // SMALL-SCENE TABLES IN THE CONSTANT BANK.  The linear-filter kernels only run scenes with <= RTRB_APEX_MAX
+  // spheres (+ boxes), <= RTRB_K_PLANES planes and <= RTRB_K_LIGHTS lights, and read every per-ray table from
+  // here instead of global memory: uniform LDC/LDCU instead of LDG (L1 is cold at every launch boundary, and a
+  // frame is one ~0.1 ms launch).  The BVH kernels ignore these fields.
+  float4 k_light_tab[RTRB_K_LIGHTS][RTRB_APEX_MAX];  // apex tables of the lights (padding: Kq = +inf)
+  float4 k_cull_sph[RTRB_APEX_MAX];                  // = cull_sph[]
+  float4 k_cull_pl[2 * RTRB_K_PLANES];               // = cull_pl[]
+  DevLight k_lights[RTRB_K_LIGHTS];                  // = lights[]
+  DevLightF k_lights_f[RTRB_K_LIGHTS];               // = lights_f[]
+  int32_t k_pl_index[RTRB_K_PLANES];                 // = pl_index[]
+  int32_t k_has_light_tab, pad_k;
 };
 
 #define RTRB_HOT_SLICES 64     // one atomic per warp lands on one of 64 address pairs (no L2 atomic hot spot)

@@ -324,3 +324,46 @@ def test_mt19937_stream_mode_matches_oracle(oracle_mod, config_id, kw, window):
     if window:
         ctr.rgb = ctr.rgb[y0:y1, x0:x1]
     assert not np.array_equal(ctr.rgb, got.rgb)  # a different stream than the counter RNG
+
+
+def _tiny_world(objects, lights):
+    from raytracing_rb_b200 import World
+    return World({"max_distance": 10000, "soft_shadow_exponent": 2, "lights": lights, "world_objects": objects})
+
+
+@pytest.mark.parametrize("precision", [PREC_STRICT, PREC_FAST64])
+@pytest.mark.parametrize("case", ["empty_world", "no_lights", "one_pixel", "ragged_37x19", "max_below_pre", "behind_camera"])
+def test_edge_cases_match_oracle(oracle_mod, case, precision):
+    """Empty and ragged inputs: no objects, no lights (every hit falls through to the Monte-Carlo branch and emits
+    no colour, ray_tracer.rb:124-142), a 1x1 frame, a frame that is not a multiple of the 32-pixel super-tile or
+    the 8x4 warp block, max_sample_times < pre_sample_times (empty extra loop, camera.rb:89-93 still rescales),
+    and a scene entirely behind the camera."""
+    from raytracing_rb_b200 import Camera, scenes
+    _, cdoc = scenes.build(3, width=64, height=36)
+    objs = [scenes.ground(), scenes.matte("a", (5, 0, -0.3), 0.7, (1, 0.5, 0.3)), scenes.glass("b", (4, 1.2, -0.6), 0.4)]
+    lights = [scenes.light([5, -4, 4], 0.8)]
+    if case == "empty_world":
+        objs = []
+    elif case == "no_lights":
+        lights = []
+        cdoc = dict(cdoc, monte_carlo_diffusion_times=2, trace_depth=3)
+    elif case == "one_pixel":
+        cdoc = dict(cdoc, width=1, height=1)
+    elif case == "ragged_37x19":
+        cdoc = dict(cdoc, width=37, height=19)
+    elif case == "max_below_pre":
+        cdoc = dict(cdoc, pre_sample_times=4, max_sample_times=2, variant_threshold=0.0)
+    elif case == "behind_camera":
+        objs = [scenes.matte("a", (-5, 0, 0), 1.0, (1, 1, 1))]
+    world = _tiny_world(objs, lights)
+    cam = Camera(world, cdoc)
+    ref = oracle_mod.OracleScene(world.to_scene_desc()).render(cam.camera_desc(), make_opts(seed=11))
+    got = cam.render_frame(seed=11, precision=precision, count_detail=True)
+    check(ref, got, precision == PREC_STRICT)
+    assert got.stats["samples"] == ref.stats["samples"] > 0
+    if case == "empty_world":
+        assert got.stats["hits"] == 0 and not got.rgba[..., :3].any() and (got.hit == -1).all()
+    if case == "no_lights":
+        assert got.stats["mc_rays"] == ref.stats["mc_rays"] > 0 and got.stats["local_shaded"] == 0
+    if case == "max_below_pre":
+        assert got.stats["adaptive_pixels"] == cdoc["width"] * cdoc["height"]  # variance >= 0.0 always
