@@ -367,3 +367,24 @@ def test_edge_cases_match_oracle(oracle_mod, case, precision):
         assert got.stats["mc_rays"] == ref.stats["mc_rays"] > 0 and got.stats["local_shaded"] == 0
     if case == "max_below_pre":
         assert got.stats["adaptive_pixels"] == cdoc["width"] * cdoc["height"]  # variance >= 0.0 always
+
+
+@pytest.mark.parametrize("config_id,kw,spp_hi", [
+    (4, dict(width=160, height=90), 512),   # soft shadows, 16 spp, Monte-Carlo diffuse rays
+    (3, dict(width=160, height=90), 256),   # depth 8 through the aperture, 4 spp
+    (1, {}, 256),                           # reference default scene, adaptive 3..10 spp
+])
+def test_stochastic_configs_psnr_vs_high_spp_reference(oracle_mod, config_id, kw, spp_hi):
+    """BASELINE.json tier 3: the stochastic configs, rendered on the GPU at their configured sample counts, reach
+    PSNR >= 40 dB against a high-spp render of the reference algorithm (the CPU oracle, a different seed)."""
+    from helpers_rtrb import psnr_u8
+    from raytracing_rb_b200 import Camera, World, scenes
+    wdoc, cdoc = scenes.build(config_id, **kw)
+    world = World(wdoc)
+    got = Camera(world, cdoc).render_frame(seed=1, want_rgb=False, want_hit=False)
+    hi_doc = dict(cdoc, pre_sample_times=spp_hi, max_sample_times=spp_hi)
+    ref = oracle_mod.OracleScene(world.to_scene_desc()).render(Camera(world, hi_doc).camera_desc(), make_opts(seed=7),
+                                                              want_rgb=False, want_hit=False)
+    p = psnr_u8(got.rgba, ref.rgba)
+    print("config %d: PSNR %.2f dB (GPU at configured spp vs oracle at %d spp)" % (config_id, p, spp_hi))
+    assert p >= 40.0
