@@ -638,6 +638,17 @@ __device__ __forceinline__ void init_ctx(ThreadCtx& ctx, bool detail) {
   }
 }
 
+// Folds the counters / status a callee collected in its own block into the thread's.
+__device__ __forceinline__ void merge_ctx(ThreadCtx& ctx, const ThreadCtx& t) {
+  ctx.status |= t.status;
+  ctx.rays += t.rays; ctx.shadow += t.shadow;
+  if (t.max_stack > ctx.max_stack) ctx.max_stack = t.max_stack;
+  if (ctx.detail) {
+#pragma unroll
+    for (int i = 0; i < RTRB_CNT_N; ++i) ctx.c[i] += t.c[i];
+  }
+}
+
 // FAST64 entry point, defined in rtrb_trace_fast.cuh (only instantiated by that translation unit).
 template <int MAXS, bool BVH, bool BOX>
 __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,

@@ -177,6 +177,29 @@ static __device__ __noinline__ int closest_hit_scan(const FrameParams& P, d3 o, 
   return best_i;
 }
 
+// The out-of-line fallbacks get TEMPORARIES for everything they take by reference: a thread's own hit record and
+// counter block must never have their address taken, or they live in local memory for the whole kernel (ncu:
+// 36 local loads/stores per thread on the config 2 kernel before this) instead of registers.
+template <bool BOX>
+__device__ __forceinline__ int closest_hit_scan_call(const FrameParams& P, d3 o, d3 d, HitRec& bh, ThreadCtx& ctx) {
+  HitRec h;
+  h.p = mk(0, 0, 0); h.dir_in = false; h.face = 0;
+  ThreadCtx t;
+  init_ctx(t, ctx.detail);
+  const int i = closest_hit_scan<BOX>(P, o, d, h, t);
+  if (i >= 0) keep_hit<BOX>(bh, h);
+  merge_ctx(ctx, t);
+  return i;
+}
+template <bool BOX>
+__device__ __forceinline__ double lit_area_call(const FrameParams& P, d3 target, const DevLight& L, ThreadCtx& ctx) {
+  ThreadCtx t;
+  init_ctx(t, ctx.detail);
+  const double a = lit_area<BOX>(P, target, L, t);
+  merge_ctx(ctx, t);
+  return a;
+}
+
 // ---- sphere BVH traversal (filter only; see rtrb_bvh.h for why it cannot change a result) ----------
 struct BvhRay {
   float ox, oy, oz, ix, iy, iz, E;
@@ -255,7 +278,7 @@ __device__ __forceinline__ bool bvh_traverse(const FrameParams& P, const BvhRay&
 template <bool BOX>
 __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx) {
-  if (P.n_sph > 0xFFFFF || P.n_pl > 8) return closest_hit_scan<BOX>(P, o, d, bh, ctx);
+  if (P.n_sph > 0xFFFFF || P.n_pl > 8) return closest_hit_scan_call<BOX>(P, o, d, bh, ctx);
   // pass 1a: planes bound the search first (nothing at or beyond max_distance can win, world.rb:39)
   float best_hi = P.max_distance_f;
   for (int k = 0; k < P.n_pl; ++k) {
@@ -277,7 +300,7 @@ __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d,
         if (kind == 2 && hi < best_hi) { best_hi = hi; tmax = hi + r.E; }
       }
     });
-    if (!ok || S.overflow()) return closest_hit_scan<BOX>(P, o, d, bh, ctx);
+    if (!ok || S.overflow()) return closest_hit_scan_call<BOX>(P, o, d, bh, ctx);
   }
   // pass 2: exact FP64 evaluation of whatever can still win; (distance, index) lexicographic order
   // reproduces the strict `<` scan in world_objects order.
@@ -336,7 +359,7 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
     const float lx = (float)c.lt.x, ly = (float)c.lt.y, lz = (float)c.lt.z;
     far = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) * 1.00001f + 2.0f * r.E;
   }
-  if (P.n_sph > 0xFFFFF || P.n_pl > 0xFFFF) return lit_area<BOX>(P, target, L, ctx);
+  if (P.n_sph > 0xFFFFF || P.n_pl > 0xFFFF) return lit_area_call<BOX>(P, target, L, ctx);
   Pack8 S, Q;
   S.clear();
   Q.clear();
@@ -349,14 +372,14 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
       const int kind = classify_sphere<BOX>(s, r, lo, hi);
       if (kind != 0 && !(lo > far)) S.push(k);
     });
-    if (!ok) return lit_area<BOX>(P, target, L, ctx);
+    if (!ok) return lit_area_call<BOX>(P, target, L, ctx);
   }
   for (int k = 0; k < P.n_pl; ++k) {
     float lo, hi;
     const int kind = classify_plane(__ldg(&P.cull_pl[2 * k]), __ldg(&P.cull_pl[2 * k + 1]), r, lo, hi);
     if (kind != 0 && !(lo > far)) Q.push((uint32_t)k);
   }
-  if (S.overflow() || Q.overflow()) return lit_area<BOX>(P, target, L, ctx);
+  if (S.overflow() || Q.overflow()) return lit_area_call<BOX>(P, target, L, ctx);
   double total = 1;
   bool have_n = false;
   // visit the survivors in ascending world_objects index (selection over <= 16 entries)
@@ -455,7 +478,7 @@ __device__ __forceinline__ uint32_t line_survivors_light(const FrameParams& P, c
 template <bool BOX, bool KT>
 __device__ __forceinline__ int closest_hit_linear(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx, const bool through_lens) {
-  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > RTRB_K_PLANES) return closest_hit_scan<BOX>(P, o, d, bh, ctx);
+  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > RTRB_K_PLANES) return closest_hit_scan_call<BOX>(P, o, d, bh, ctx);
   const uint32_t mask = (through_lens && P.cam_tab_valid) ? line_survivors_camera(P, r) : line_survivors_generic<KT>(P, r);
   // pass 1 (only when something can be pruned): the smallest certain upper bound; nothing at or beyond
   // max_distance can win (world.rb:39)
@@ -528,7 +551,7 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
     const float lx = (float)c.lt.x, ly = (float)c.lt.y, lz = (float)c.lt.z;
     far = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) * 1.00001f + 2.0f * r.E;
   }
-  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > RTRB_K_PLANES) return lit_area<BOX>(P, target, L, ctx);
+  if (P.n_sph > RTRB_APEX_MAX || P.n_pl > RTRB_K_PLANES) return lit_area_call<BOX>(P, target, L, ctx);
   // the probe ray's line passes through the light: apex table of this light when there is one
   uint32_t sm = (P.k_has_light_tab != 0) ? line_survivors_light<KT>(P, light_index, r) : line_survivors_generic<KT>(P, r);
   uint32_t qm = 0u;
