@@ -610,7 +610,7 @@ __device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, 
   if (lane == 0) {
     // one fire-and-forget RED per warp and counter, spread over RTRB_HOT_SLICES address pairs (the host
     // sums the slices): no block barrier, and no single L2 line taking 65 K atomics per frame
-    unsigned long long* hot = P.hot + 2u * (((blockIdx.x << 2) | (threadIdx.x >> 5)) & (RTRB_HOT_SLICES - 1));
+    unsigned long long* hot = P.hot + 2u * ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (RTRB_HOT_SLICES - 1));
     if (rays) atomicAdd(&hot[0], (unsigned long long)rays);
     if (shadow) atomicAdd(&hot[1], (unsigned long long)shadow);
     if (ms > 1u) atomicMax(&P.status[1], ms);  // 1 (just the root) is the host-side default

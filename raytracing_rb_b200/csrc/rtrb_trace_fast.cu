@@ -5,20 +5,33 @@
 
 namespace {
 
+// Launch shape per kernel family (both are 16 warps per SM at 128 registers; measured on B200, profiles/README.md):
+//   depth-1 kernels (MAXS == 1): 128 threads x 4 CTAs per SM  (256 x 2 is 5 % slower on config 2)
+//   ray-tree kernels (MAXS > 1): 256 threads x 2 CTAs per SM with the linear filter on frames of more than a few
+//                                waves (4-6 % faster on configs 3/4); 128 x 4 with the BVH filter (256 x 2 is 5 %
+//                                slower on config 5) and on small frames (config 1).  Same register cap either
+//                                way, so one compiled kernel serves both shapes and the launcher picks.
 #ifndef RTRB_FAST_BLOCK
 #define RTRB_FAST_BLOCK 128
 #endif
-constexpr int kBlock = RTRB_FAST_BLOCK;
 #ifndef RTRB_FAST_MIN_BLOCKS
 #define RTRB_FAST_MIN_BLOCKS 4
 #endif
+#ifndef RTRB_TREE_BLOCK
+#define RTRB_TREE_BLOCK 256
+#endif
+#ifndef RTRB_TREE_MIN_BLOCKS
+#define RTRB_TREE_MIN_BLOCKS 2
+#endif
+template <int MAXS> constexpr int block_of() { return MAXS == 1 ? RTRB_FAST_BLOCK : RTRB_TREE_BLOCK; }
+template <int MAXS> constexpr int min_blocks_of() { return MAXS == 1 ? RTRB_FAST_MIN_BLOCKS : RTRB_TREE_MIN_BLOCKS; }
 
 template <int MAXS, bool DETAIL, bool BVH>
-__global__ void __launch_bounds__(kBlock, RTRB_FAST_MIN_BLOCKS) trace_pre_fast_kernel(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(block_of<MAXS>(), min_blocks_of<MAXS>()) trace_pre_fast_kernel(const __grid_constant__ FrameParams P) {
   rtrb::trace_pre_body<MAXS, DETAIL, BVH ? 2 : 1>(P);
 }
 template <int MAXS, bool DETAIL, bool BVH>
-__global__ void __launch_bounds__(kBlock, RTRB_FAST_MIN_BLOCKS) trace_extra_fast_kernel(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(block_of<MAXS>(), min_blocks_of<MAXS>()) trace_extra_fast_kernel(const __grid_constant__ FrameParams P) {
   rtrb::trace_extra_body<MAXS, DETAIL, BVH ? 2 : 1>(P);
 }
 
@@ -31,6 +44,8 @@ template <int MAXS, bool DETAIL>
 cudaError_t launch_pre(const FrameParams& P, cudaStream_t s) {
   unsigned long long total = (unsigned long long)P.n_tiles * RTRB_SUPER_PIXELS * (unsigned long long)P.pre;
   if (total == 0) return cudaSuccess;
+  int kBlock = block_of<MAXS>();
+  if (kBlock > 128 && (P.use_bvh || total < 4ull * 148ull * 2ull * 256ull)) kBlock = 128;
   unsigned long long blocks = (total + kBlock - 1) / kBlock;
   if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   if (P.use_bvh) trace_pre_fast_kernel<MAXS, DETAIL, true><<<(unsigned)blocks, kBlock, 0, s>>>(P);
@@ -42,6 +57,7 @@ cudaError_t launch_extra(const FrameParams& P, cudaStream_t s) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  constexpr int kBlock = 128;
   if (P.use_bvh) trace_extra_fast_kernel<MAXS, DETAIL, true><<<sms * 8, kBlock, 0, s>>>(P);
   else trace_extra_fast_kernel<MAXS, DETAIL, false><<<sms * 8, kBlock, 0, s>>>(P);
   return cudaGetLastError();
