@@ -187,7 +187,7 @@ def bind_to_gpu_numa_node(index):
 
 def run_ours(args, rank, local_rank, world_size):
     import torch
-    from raytracing_rb_b200 import (Renderer, _abi, ipc_open, make_opts, measure_fma_peak, PREC_FAST64, PREC_STRICT)
+    from raytracing_rb_b200 import (Renderer, _abi, deal_frames, ipc_open, make_opts, measure_fma_peak, PREC_FAST64, PREC_STRICT)
     from raytracing_rb_b200._lib import lib
 
     if not torch.cuda.is_available():
@@ -226,8 +226,9 @@ def run_ours(args, rank, local_rank, world_size):
         slots = list(range(B))
         n_slots = B
     else:
-        cams = batch_cameras(world, cdoc, B, rank * B)  # rank r: frames [r*B, (r+1)*B), whole
-        slots = [rank * B + f for f in range(B)]
+        dealt = deal_frames(rank, world_size, B)        # rank r: frames [r*B, (r+1)*B), whole
+        cams = batch_cameras(world, cdoc, B, dealt[0][0] if dealt else 0)
+        slots = [slot for _, slot in dealt]
         n_slots = B * world_size
     W, H = cams[0].width, cams[0].height
     slot_bytes = W * H * 4           # slots are sized for RGBA8 whatever the format

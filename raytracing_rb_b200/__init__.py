@@ -10,7 +10,7 @@ from .camera import Camera, write_png
 from .configurable_object import ConfigurableObject
 from .lights import Light, SpotLight
 from .objects import Box, Plane, Sphere, WorldObject
-from .renderer import (Frame, Renderer, device_count, ipc_close, ipc_open, make_opts, measure_fma_peak,
+from .renderer import (Frame, Renderer, deal_frames, device_count, ipc_close, ipc_open, make_opts, measure_fma_peak,
                        render_multi, tile_partition)
 from .texture import Texture
 from .vec3 import Vec3
@@ -19,6 +19,6 @@ from .world import World
 __all__ = [
     "Camera", "World", "Sphere", "Plane", "Box", "WorldObject", "Light", "SpotLight", "Texture", "Vec3",
     "ConfigurableObject", "Renderer", "Frame", "make_opts", "render_multi", "measure_fma_peak",
-    "device_count", "ipc_open", "ipc_close", "write_png", "tile_partition",
+    "device_count", "deal_frames", "ipc_open", "ipc_close", "write_png", "tile_partition",
     "PREC_STRICT", "PREC_FAST64", "PREC_DEFAULT", "RNG_CTR", "RNG_MT",
 ]

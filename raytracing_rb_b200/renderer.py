@@ -172,6 +172,16 @@ def tile_partition(width, height, tile_rank=0, tile_world=1, window=None):
     return list(out[:n.value])
 
 
+def deal_frames(rank, world, frames_per_gpu):
+    """Whole-frame dealing of a batch of small frames: rank r renders frames
+    [r*B, (r+1)*B) of the step and frame f lands in slot f of rank 0's framebuffer.  Returns the list of
+    (frame index, slot) pairs of `rank`.  Pure host logic."""
+    if world < 1 or not 0 <= rank < world or frames_per_gpu < 0:
+        raise ValueError("bad rank/world/frames_per_gpu")
+    first = rank * frames_per_gpu
+    return [(first + f, first + f) for f in range(frames_per_gpu)]
+
+
 def measure_fma_peak(device=0, fp64=True):
     v = C.c_double()
     check(lib().rtrb_measure_fma_peak(device, 1 if fp64 else 0, C.byref(v)))

@@ -1,6 +1,7 @@
 """N > 1 host logic on CPU: two `gloo` ranks (world_size 2, 127.0.0.1) each ask the C ABI for their
 share of a frame's 32x32 super-tiles; together the shares must cover every tile exactly once, for
-full frames, ragged sizes and column-strip windows.  No GPU work happens here."""
+full frames, ragged sizes and column-strip windows; and the whole-frame dealing of a batch must give every
+frame slot to exactly one rank.  No GPU work happens here."""
 import os
 import socket
 import subprocess
@@ -13,7 +14,7 @@ import os, sys
 sys.path.insert(0, %r)
 import torch
 import torch.distributed as dist
-from raytracing_rb_b200 import tile_partition
+from raytracing_rb_b200 import deal_frames, tile_partition
 
 dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
@@ -36,6 +37,16 @@ for (w, h, win) in cases:
     n = torch.tensor([len(mine)]); lo = n.clone(); hi = n.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert int(hi) - int(lo) <= 1
+# whole-frame dealing of a batch (bench.py's default at N > 1): every frame of the step is rendered by exactly one
+# rank and lands in its own slot of rank 0's framebuffer
+for B in (1, 16, 5):
+    mine = deal_frames(rank, world, B)
+    t = torch.zeros(world * B, dtype=torch.int32)
+    for frame, slot in mine:
+        assert frame == slot
+        t[slot] += 1
+    dist.all_reduce(t)
+    assert torch.equal(t, torch.ones_like(t)), B
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
