@@ -10,7 +10,9 @@
 //     ext/fast_4d_matrix/fast_4d_matrix.c (compiled unmodified against oracle/ruby_shim/ruby.h
 //     into oracle/_ref/) against these functions and against the 19 RSpec known answers;
 //   * the renderer above Vec3 is "parity unpinned": it is a line-by-line restatement checked by
-//     the hand-derived known answers of SURVEY.md 8c (tests/test_oracle_kat.py).
+//     the hand-derived known answers of SURVEY.md 8c (tests/test_oracle_kat.py, test_oracle_box_kat.py),
+//     cross-checked bit for bit against a second, independently written restatement
+//     (oracle/restate_py.py, tests/test_restatements_agree.py), and frozen in tests/golden/.
 //
 // Every function cites the reference lines it follows (paths relative to /root/reference).
 // The style is deliberately literal: a Vec3 carries its cached norm exactly like the C ext, and
