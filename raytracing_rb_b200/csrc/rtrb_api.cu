@@ -232,23 +232,36 @@ using rtrb::pre_mean;
 
 __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ FrameParams P) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= (uint32_t)P.n_tiles * RTRB_SUPER_PIXELS) return;
-  int x, y;
-  if (!slot_to_xy(P, slot, x, y)) return;
-  double ax, ay, az, variance;
-  pre_mean(P, slot, ax, ay, az, variance);
-  if (variance >= P.variant_threshold) {
-    atomicAdd(&P.counters[RTRB_CNT_ADAPTIVE], 1ull);
-    if (P.max_samples > P.pre) {
-      uint32_t e = atomicAdd(P.extra_count, 1u);
-      P.extra_list[e] = slot;
-      return;  // finished by resolve_extra_kernel
+  int x = 0, y = 0;
+  const bool valid = slot < (uint32_t)P.n_tiles * RTRB_SUPER_PIXELS && slot_to_xy(P, slot, x, y);
+  double ax = 0, ay = 0, az = 0, variance = 0;
+  if (valid) pre_mean(P, slot, ax, ay, az, variance);
+  const bool adaptive = valid && variance >= P.variant_threshold;
+  // warp-level compaction of the pixels that take the extra-sample branch (camera.rb:87-93): one ballot over
+  // the whole warp, one atomic per warp for the counter and one for the list, each lane's list position from a
+  // prefix popcount of the ballot
+  const unsigned amask = __ballot_sync(0xffffffffu, adaptive);
+  uint32_t base = 0;
+  if (amask != 0u) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(amask) - 1;
+    if (lane == leader) {
+      const uint32_t n = __popc(amask);
+      atomicAdd(&P.counters[RTRB_CNT_ADAPTIVE], (unsigned long long)n);
+      if (P.max_samples > P.pre) base = atomicAdd(P.extra_count, n);
     }
-    // empty extra loop: (average * pre + 0) / max  (camera.rb:93)
-    const double fp = (double)P.pre, fm = (double)P.max_samples;
-    ax = (ax * fp + 0.0) / fm; ay = (ay * fp + 0.0) / fm; az = (az * fp + 0.0) / fm;
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (adaptive) {
+      if (P.max_samples > P.pre) {
+        P.extra_list[base + __popc(amask & ((1u << lane) - 1u))] = slot;
+        return;  // finished by resolve_extra_kernel
+      }
+      // empty extra loop: (average * pre + 0) / max  (camera.rb:93)
+      const double fp = (double)P.pre, fm = (double)P.max_samples;
+      ax = (ax * fp + 0.0) / fm; ay = (ay * fp + 0.0) / fm; az = (az * fp + 0.0) / fm;
+    }
   }
-  write_pixel(P, x, y, ax, ay, az);
+  if (valid) write_pixel(P, x, y, ax, ay, az);
 }
 
 __global__ void __launch_bounds__(256) resolve_extra_kernel(const __grid_constant__ FrameParams P) {
