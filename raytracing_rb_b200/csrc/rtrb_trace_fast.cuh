@@ -461,14 +461,14 @@ __device__ __forceinline__ uint32_t line_survivors_light(const FrameParams& P, c
     const float4* tab = P.light_tab + (size_t)light_index * P.n_sph;
 #pragma unroll 4
     for (int k = 0; k < P.n_sph; ++k) m |= apex_test(__ldg(&tab[k]), r) << k;
-    return m;
-  }
-  // constant-bank table, eight spheres per uniform branch like the camera table
+  } else {
+    // constant-bank table, eight spheres per uniform branch like the camera table
 #pragma unroll
-  for (int blk = 0; blk < RTRB_APEX_MAX / 8; ++blk) {
-    if (blk * 8 < P.n_sph) {
+    for (int blk = 0; blk < RTRB_APEX_MAX / 8; ++blk) {
+      if (blk * 8 < P.n_sph) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m |= apex_test(P.k_light_tab[light_index][blk * 8 + j], r) << (blk * 8 + j);
+        for (int j = 0; j < 8; ++j) m |= apex_test(P.k_light_tab[light_index][blk * 8 + j], r) << (blk * 8 + j);
+      }
     }
   }
   return m;
