@@ -670,7 +670,7 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
         if (highlight_match_fast(light_at<KT>(P, l), light_f_at<KT>(P, l), o, d, r, ctx)) { hl_mask |= 1ull << l; hl_n++; }
       if (hl_n > 0) {
         for (int l = 0; l < P.n_lights; ++l) {
-          if (!((hl_mask >> l) & 1ull)) return;
+          if (!((hl_mask >> l) & 1ull)) continue;
           d3 c = att * ld3(light_at<KT>(P, l).color_hl);
           if (hl_n != 1) c = c / (double)hl_n;  // x / 1.0 == x
           sum = sum + c;
