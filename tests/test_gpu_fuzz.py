@@ -74,3 +74,65 @@ def test_random_scene_parity(oracle_mod, seed):
     print("seed %d kind %d: %d objects, depth %d, rays %d, status %d, exact tests/query %.2f" % (
         seed, seed % 6, len(wdoc["world_objects"]), cdoc["trace_depth"], a.stats["rays"], a.stats["status"],
         b.stats["exact_tests"] / max(1, b.stats["rays"] + b.stats["shadow_queries"])))
+
+
+def structural_scene(seed):
+    """Scenes that sit on the dispatch boundaries of the CUDA path: 31-34 spheres (linear filter vs BVH), 8-10 planes
+    (constant tables vs fallback scan), 0-3 lights, cameras with unnormalised / tilted axes, odd frame sizes."""
+    rs = np.random.RandomState(1000 + seed)
+    n_sph = [0, 1, 31, 32, 33, 34, 40, 5][seed % 8]
+    n_pl = [1, 2, 8, 9, 10, 1, 0, 3][(seed // 2) % 8]
+    n_li = [1, 0, 2, 3, 1, 2][seed % 6]
+    objs = []
+    for k in range(n_pl):
+        pl = scenes.ground()
+        pl["properties"]["name"] = "pl%d" % k
+        if k > 0:
+            pl["properties"].update({"point": [float(rs.uniform(8, 20)), float(rs.uniform(-6, 6)), float(rs.uniform(-3, 3))],
+                                     "front": [float(v) for v in rs.uniform(-1, 1, 3)], "up": [float(v) for v in rs.uniform(-1, 1, 3)]})
+        objs.append(pl)
+    for i in range(n_sph):
+        r = float(rs.uniform(0.15, 0.5))
+        c = [rs.uniform(3, 14), rs.uniform(-5, 5), rs.uniform(-1 + r, 2)]
+        objs.append(scenes.glass("g%d" % i, c, r) if i % 3 == 0 else scenes.matte("m%d" % i, c, r, rs.uniform(0.3, 1, 3)))
+    if seed % 5 == 0:
+        objs.insert(len(objs) // 2, scenes.box("bx", [6, 0.5, 0], [1, 0.2, 0], [0, 0, 1], (0.8, 0.9, 0.7)))
+    spots = ([5, -4, 4], [2, 5, 6], [8, 0.5, 3])
+    lights = [scenes.light(spots[i], float(rs.choice([0.0, 0.6]))) for i in range(n_li)]
+    for l in lights:
+        l["properties"]["color"] = [1.0 / max(1, n_li)] * 3
+    world = {"max_distance": 10000, "soft_shadow_exponent": [2, 2, 1.5][seed % 3], "lights": lights, "world_objects": objs}
+    cam = dict(scenes.COMMON_CAMERA, width=int(rs.choice([33, 64, 95])), height=int(rs.choice([17, 36, 50])),
+               pre_sample_times=int(rs.choice([1, 3])), max_sample_times=int(rs.choice([3, 6])),
+               variant_threshold=float(rs.choice([0.0005, 0.02])), trace_depth=int(rs.randint(1, 5)),
+               monte_carlo_diffusion_times=int(rs.choice([0, 1])), aperture_radius=float(rs.choice([0.0, 0.002])))
+    if seed % 4 == 1:
+        cam.update(front=[2.0, 0.5, 0.1], up=[0.0, 0.0, 3.0])          # unnormalised, not quite orthogonal
+    if seed % 4 == 3:
+        cam.update(front=[1.0, 0.0, -0.3], up=[0.3, 0.0, 1.0], position=[0.0, 0.0, 1.0])
+    return world, cam
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_structural_scene_parity(oracle_mod, seed):
+    wdoc, cdoc = structural_scene(seed)
+    world = World(wdoc)
+    cam = Camera(world, cdoc)
+    a = cam.render_frame(seed=7, precision=PREC_STRICT, count_detail=True)
+    b = cam.render_frame(seed=7, precision=PREC_FAST64, count_detail=True)
+    assert np.array_equal(a.rgb, b.rgb, equal_nan=True), "FAST64 must equal STRICT bit for bit"
+    assert np.array_equal(a.rgba, b.rgba) and np.array_equal(a.hit, b.hit)
+    for k in ("samples", "rays", "shadow_queries", "hits", "highlight_hits", "local_shaded", "lit_lights", "mc_rays",
+              "adaptive_pixels", "status"):
+        assert a.stats[k] == b.stats[k], k
+    ref = oracle_mod.OracleScene(world.to_scene_desc()).render(cam.camera_desc(), make_opts(seed=7))
+    d = np.abs(a.rgba.astype(np.int16) - ref.rgba.astype(np.int16))
+    assert (d.max(axis=-1) <= 1).mean() >= 0.999, "max abs diff %d" % d.max()
+    assert np.array_equal(a.hit, ref.hit)
+    for k in ("samples", "rays", "shadow_queries", "hits", "refractions", "mc_rays", "adaptive_pixels", "status"):
+        assert a.stats[k] == ref.stats[k], k
+    # the lean (no detail counters) FAST64 kernels and the RGB8 layout must give the same bytes
+    from raytracing_rb_b200 import _abi
+    lean = cam.renderer().render(cam.camera_desc(), make_opts(seed=7, pixel_format=_abi.FMT_RGB8), want_rgb=False, want_hit=False)
+    assert np.array_equal(lean.rgba, b.rgba[..., :3])
+    assert lean.stats["rays"] == b.stats["rays"] and lean.stats["shadow_queries"] == b.stats["shadow_queries"]
