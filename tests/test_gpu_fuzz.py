@@ -136,3 +136,58 @@ def test_structural_scene_parity(oracle_mod, seed):
     lean = cam.renderer().render(cam.camera_desc(), make_opts(seed=7, pixel_format=_abi.FMT_RGB8), want_rgb=False, want_hit=False)
     assert np.array_equal(lean.rgba, b.rgba[..., :3])
     assert lean.stats["rays"] == b.stats["rays"] and lean.stats["shadow_queries"] == b.stats["shadow_queries"]
+
+
+def material_scene(seed):
+    """Textures with odd scales / negative offsets on planes and spheres, highlight angles from 0 to beyond 90
+    degrees, point and very wide lights, soft_shadow_exponent other than 2 (the libm pow path), a short max_distance
+    that cuts far hits off, refractive rates below 1, deep trees."""
+    rs = np.random.RandomState(5000 + seed)
+    objs = [scenes.ground()]
+    w = scenes.wall(float(rs.uniform(9, 16)))
+    w["properties"].update({"texture_horizontal_scale": float(rs.choice([0.015, 0.0037, 0.11])),
+                            "texture_vertical_scale": float(rs.choice([0.015, 0.0051, 0.2]))})
+    if seed % 3 == 0:
+        w["properties"].update({"refractive_rate": float(rs.choice([0.8, 1.3])), "refractive_attenuation": [0.1, 0.1, 0.1],
+                                "diffuse_rate": [0.5, 0.5, 0.5]})
+    objs.append(w)
+    for i in range(int(rs.randint(2, 7))):
+        r = float(rs.uniform(0.3, 0.9))
+        c = [rs.uniform(3, 8), rs.uniform(-3, 3), -1 + r]
+        if i % 3 == 0:
+            o = scenes.matte("t%d" % i, c, r, (1, 1, 1))
+            o["properties"].update({"greenwich_vec": [float(v) for v in rs.uniform(-1, 1, 3)], "north_pole_vec": [0.2, 0.1, 1.0],
+                                    "texture_file_path": scenes.TEXTURE, "texture_horizontal_scale": float(rs.choice([0.0082, 0.05])),
+                                    "texture_vertical_scale": float(rs.choice([0.0063, 0.02])),
+                                    "texture_u_offset": float(rs.uniform(-2, 2)), "texture_v_offset": float(rs.uniform(-2, 2))})
+        else:
+            o = scenes.glass("g%d" % i, c, r)
+            o["properties"]["refractive_rate"] = float(rs.choice([1.6, 0.8, 1.05, 2.4]))
+        objs.append(o)
+    lights = [scenes.light([5, -4, 4], float(rs.choice([0.0, 0.8, 3.0])))]
+    lights[0]["properties"].update({"high_light_angle": float(rs.choice([0, 3, 45, 90, 120])), "high_light_rate": float(rs.choice([1, 0.5]))})
+    world = {"max_distance": float(rs.choice([10000, 9.0])), "soft_shadow_exponent": float(rs.choice([2, 1, 3.7])),
+             "lights": lights, "world_objects": objs}
+    cam = dict(scenes.COMMON_CAMERA, width=80, height=45, pre_sample_times=2, max_sample_times=4,
+               variant_threshold=0.01, trace_depth=int(rs.choice([2, 5, 8])), monte_carlo_diffusion_times=int(rs.choice([0, 1])))
+    return world, cam
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_material_scene_parity(oracle_mod, seed):
+    wdoc, cdoc = material_scene(seed)
+    world = World(wdoc)
+    cam = Camera(world, cdoc)
+    a = cam.render_frame(seed=3, precision=PREC_STRICT, count_detail=True)
+    b = cam.render_frame(seed=3, precision=PREC_FAST64, count_detail=True)
+    assert np.array_equal(a.rgb, b.rgb, equal_nan=True), "FAST64 must equal STRICT bit for bit"
+    assert np.array_equal(a.rgba, b.rgba) and np.array_equal(a.hit, b.hit)
+    ref = oracle_mod.OracleScene(world.to_scene_desc()).render(cam.camera_desc(), make_opts(seed=3))
+    d = np.abs(a.rgba.astype(np.int16) - ref.rgba.astype(np.int16))
+    assert (d.max(axis=-1) <= 1).mean() >= 0.999, "max abs diff %d" % d.max()
+    assert np.array_equal(a.hit, ref.hit)
+    for k in ("samples", "rays", "shadow_queries", "hits", "highlight_hits", "refractions", "mc_rays", "texel_fetches",
+              "adaptive_pixels", "status"):
+        assert a.stats[k] == ref.stats[k], k
+        if k != "refractions":
+            assert b.stats[k] == ref.stats[k], k
