@@ -191,3 +191,20 @@ def test_material_scene_parity(oracle_mod, seed):
         assert a.stats[k] == ref.stats[k], k
         if k != "refractions":
             assert b.stats[k] == ref.stats[k], k
+
+
+@pytest.mark.parametrize("seed", [1, 5, 8, 11])  # (seed 20 also passes: 3 763 passes, 40 s)
+def test_random_scene_mt_stream_mode(oracle_mod, seed):
+    """The MT19937 stream mode on randomised scenes (several lights, boxes, Monte-Carlo rays, adaptive sampling):
+    the frame, the hit ids and the counters must equal the oracle's MT frame."""
+    from raytracing_rb_b200 import RNG_MT
+    wdoc, cdoc = random_scene(seed)
+    world = World(wdoc)
+    cam = Camera(world, cdoc)
+    ref = oracle_mod.OracleScene(world.to_scene_desc()).render(cam.camera_desc(), make_opts(seed=1, rng_mode=RNG_MT), threads=1)
+    got = cam.render_frame(seed=1, rng_mode=RNG_MT, count_detail=True)
+    d = np.abs(got.rgba.astype(np.int16) - ref.rgba.astype(np.int16))
+    assert (d.max(axis=-1) <= 1).mean() >= 0.999 and np.array_equal(got.hit, ref.hit)
+    for k in ("samples", "rays", "shadow_queries", "hits", "mc_rays", "adaptive_pixels", "status"):
+        assert got.stats[k] == ref.stats[k], k
+    print("seed %d: fixed point after %d passes" % (seed, cam.renderer().last_mt_passes()))
