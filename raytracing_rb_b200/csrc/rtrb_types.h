@@ -159,6 +159,8 @@ struct FrameParams {
   int32_t k_has_light_tab, pad_k;
 };
 
+static_assert(sizeof(FrameParams) <= 4096, "FrameParams must fit the 4 KB kernel-parameter space");
+
 #define RTRB_HOT_SLICES 64     // one atomic per warp lands on one of 64 address pairs (no L2 atomic hot spot)
 
 enum {
