@@ -1,16 +1,18 @@
 // rtrb_trace_fast.cu — RTRB_PREC_FAST64 instantiation (FP32 filter + exact FP64 refine).
 // Compiled with -fmad=false: the exact parts must round like STRICT; the filter uses explicit fmaf().
+#include <stdlib.h>
+
 #include "rtrb_launch.h"
 #include "rtrb_trace_fast.cuh"
 
 namespace {
 
-// Launch shape per kernel family (both are 16 warps per SM at 128 registers; measured on B200, profiles/README.md):
+// Launch shape per kernel family (16 warps per SM at 128 registers either way; measured on B200, profiles/README.md):
 //   depth-1 kernels (MAXS == 1): 128 threads x 4 CTAs per SM  (256 x 2 is 5 % slower on config 2)
-//   ray-tree kernels (MAXS > 1): 256 threads x 2 CTAs per SM with the linear filter on frames of more than a few
-//                                waves (4-6 % faster on configs 3/4); 128 x 4 with the BVH filter (256 x 2 is 5 %
-//                                slower on config 5) and on small frames (config 1).  Same register cap either
-//                                way, so one compiled kernel serves both shapes and the launcher picks.
+//   ray-tree kernels (MAXS > 1): lockstep item loop (rtrb_trace.cuh), so the CTA is the unit that shares the
+//                                instruction caches: 512 threads x 1 CTA per SM on frames of more than a few waves
+//                                (config 4: 4.44 / 3.78 / 3.57 ms and config 5: 5.13 / 4.61 / 4.24 ms with 128 / 256 /
+//                                512 threads; config 3: 3.87 / 3.44 / 3.52), 128 threads on small frames.
 #ifndef RTRB_FAST_BLOCK
 #define RTRB_FAST_BLOCK 128
 #endif
@@ -18,10 +20,10 @@ namespace {
 #define RTRB_FAST_MIN_BLOCKS 4
 #endif
 #ifndef RTRB_TREE_BLOCK
-#define RTRB_TREE_BLOCK 256
+#define RTRB_TREE_BLOCK 512
 #endif
 #ifndef RTRB_TREE_MIN_BLOCKS
-#define RTRB_TREE_MIN_BLOCKS 2
+#define RTRB_TREE_MIN_BLOCKS 1
 #endif
 template <int MAXS> constexpr int block_of() { return MAXS == 1 ? RTRB_FAST_BLOCK : RTRB_TREE_BLOCK; }
 template <int MAXS> constexpr int min_blocks_of() { return MAXS == 1 ? RTRB_FAST_MIN_BLOCKS : RTRB_TREE_MIN_BLOCKS; }
@@ -45,7 +47,11 @@ cudaError_t launch_pre(const FrameParams& P, cudaStream_t s) {
   unsigned long long total = (unsigned long long)P.n_tiles * RTRB_SUPER_PIXELS * (unsigned long long)P.pre;
   if (total == 0) return cudaSuccess;
   int kBlock = block_of<MAXS>();
-  if (kBlock > 128 && (P.use_bvh || total < 4ull * 148ull * 2ull * 256ull)) kBlock = 128;
+  if (kBlock > 128 && total < 4ull * 148ull * 512ull) kBlock = 128;  // small frames: more, smaller CTAs
+  if (MAXS > 1) {  // development override: RTRB_TREE_BLOCK_RT=<threads> (must not exceed the compiled launch bound)
+    static const int env_block = getenv("RTRB_TREE_BLOCK_RT") ? atoi(getenv("RTRB_TREE_BLOCK_RT")) : 0;
+    if (env_block >= 32 && env_block <= block_of<MAXS>() && env_block % 32 == 0) kBlock = env_block;
+  }
   unsigned long long blocks = (total + kBlock - 1) / kBlock;
   if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   if (P.use_bvh) trace_pre_fast_kernel<MAXS, DETAIL, true><<<(unsigned)blocks, kBlock, 0, s>>>(P);

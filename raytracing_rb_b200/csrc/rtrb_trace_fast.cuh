@@ -884,4 +884,34 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
   return sum;
 }
 
+#ifdef RTRB_LOCKSTEP
+template <int MAXS, bool BVH, bool BOX>
+__device__ __forceinline__ d3 trace_sample_fast_lockstep(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
+                                                         ThreadCtx& ctx, int* primary_hit, bool active) {
+  StackItem stack[MAXS > 1 ? MAXS : 1];
+  StackItem it;
+  it.ox = ro.x; it.oy = ro.y; it.oz = ro.z;
+  it.dx = rd.x; it.dy = rd.y; it.dz = rd.z;
+  it.ax = 1.0; it.ay = 1.0; it.az = 1.0;
+  it.depth = P.trace_depth; it.path = 1u;
+  int sp = 0;
+  d3 sum = mk(0.0, 0.0, 0.0);
+  bool first = true, have = active;
+  *primary_hit = -1;
+  if (active) ctx.max_stack = max(ctx.max_stack, 1u);
+  while (__syncthreads_or(have ? 1 : 0)) {
+    if (have) {
+      process_item_fast<MAXS, BVH, BOX>(P, it, stack, sp, sum, ctx, pixel, sample, first, primary_hit);
+      first = false;
+      if (sp == 0) have = false;
+      else {
+        if ((uint32_t)sp > ctx.max_stack) ctx.max_stack = (uint32_t)sp;
+        it = stack[--sp];
+      }
+    }
+  }
+  return sum;
+}
+#endif
+
 }  // namespace rtrb
