@@ -647,49 +647,61 @@ __device__ __forceinline__ bool attenuation_dead(d3 att) {
   return sqrt(s2) < 0.0001;
 }
 
-// rt_map (ray_tracer.rb:50-164) for ONE popped work item, FAST64 evaluation: pushes the children
-// onto `stack`, adds the emitted colours to `sum` in emission order.
+// rt_map (ray_tracer.rb:50-164) for ONE popped work item, FAST64 evaluation, in two phases so that the lockstep item
+// loop (rtrb_trace.cuh) can put a block barrier between them:
+//   phase A  the cut at :52, World#high_lights, World#intersect  -> index of the hit object, or -1 when the item ends
+//            here (dead, terminated by a highlight, or a miss);
+//   phase B  intersect_parameters, the children (pushed onto `stack`), World#local_lights and local_lighting.
+// Emitted colours are added to `sum` in emission order.
 template <int MAXS, bool BVH, bool BOX>
-__device__ __forceinline__ void process_item_fast(const FrameParams& P, const StackItem& it, StackItem* stack, int& sp,
-                                                  d3& sum, ThreadCtx& ctx, uint32_t pixel, uint32_t sample,
-                                                  bool is_first, int* primary_hit) {
-  const uint32_t K = (uint32_t)(P.mc + 2);
+__device__ __forceinline__ int item_phase_a(const FrameParams& P, const StackItem& it, d3& sum, ThreadCtx& ctx, bool is_first,
+                                            int* primary_hit, HitRec& bh) {
   constexpr bool KT = !BVH && MAXS == 1;  // constant-bank tables: depth-1 linear-filter kernels only (see pl_rec)
+  const d3 o = mk(it.ox, it.oy, it.oz), d = mk(it.dx, it.dy, it.dz), att = mk(it.ax, it.ay, it.az);
+  if (it.depth <= 0 || attenuation_dead(att)) return -1;  // rt_map :52
+  ctx.rays++;
+
+  const CullRay r = make_cull_ray(P, o, d);
+
+  // ---- World#high_lights ----
+  {
+    unsigned long long hl_mask = 0ull;
+    int hl_n = 0;
+    for (int l = 0; l < P.n_lights; ++l)
+      if (highlight_match_fast(light_at<KT>(P, l), light_f_at<KT>(P, l), o, d, r, ctx)) { hl_mask |= 1ull << l; hl_n++; }
+    if (hl_n > 0) {
+      for (int l = 0; l < P.n_lights; ++l) {
+        if (!((hl_mask >> l) & 1ull)) continue;
+        d3 c = att * ld3(light_at<KT>(P, l).color_hl);
+        if (hl_n != 1) c = c / (double)hl_n;  // x / 1.0 == x
+        sum = sum + c;
+        if (sum.x > 1 || sum.y > 1 || sum.z > 1) ctx.status |= RTRB_ST_COLOR_GT_1;
+      }
+      RTRB_COUNT(ctx, RTRB_CNT_HIGHLIGHT);
+      if (is_first) *primary_hit = -2;
+      return -1;
+    }
+  }
+
+  // ---- World#intersect ----
+  bh.p = mk(0, 0, 0); bh.dir_in = false;
+  if constexpr (BOX) bh.face = 0;
+  const int best_i = closest_hit_fast<BVH, BOX, KT>(P, o, d, r, bh, ctx, is_first);
+  if (best_i < 0) return -1;
+  if (is_first) *primary_hit = best_i;
+  RTRB_COUNT(ctx, RTRB_CNT_HITS);
+  return best_i;
+}
+
+template <int MAXS, bool BVH, bool BOX>
+__device__ __forceinline__ void item_phase_b(const FrameParams& P, const StackItem& it, const int best_i, const HitRec& bh,
+                                             StackItem* stack, int& sp, d3& sum, ThreadCtx& ctx, uint32_t pixel,
+                                             uint32_t sample) {
+  const uint32_t K = (uint32_t)(P.mc + 2);
+  constexpr bool KT = !BVH && MAXS == 1;
   {
     const d3 o = mk(it.ox, it.oy, it.oz), d = mk(it.dx, it.dy, it.dz), att = mk(it.ax, it.ay, it.az);
-    if (it.depth <= 0 || attenuation_dead(att)) return;  // rt_map :52
-    ctx.rays++;
-
-    const CullRay r = make_cull_ray(P, o, d);
-
-    // ---- World#high_lights ----
-    {
-      unsigned long long hl_mask = 0ull;
-      int hl_n = 0;
-      for (int l = 0; l < P.n_lights; ++l)
-        if (highlight_match_fast(light_at<KT>(P, l), light_f_at<KT>(P, l), o, d, r, ctx)) { hl_mask |= 1ull << l; hl_n++; }
-      if (hl_n > 0) {
-        for (int l = 0; l < P.n_lights; ++l) {
-          if (!((hl_mask >> l) & 1ull)) continue;
-          d3 c = att * ld3(light_at<KT>(P, l).color_hl);
-          if (hl_n != 1) c = c / (double)hl_n;  // x / 1.0 == x
-          sum = sum + c;
-          if (sum.x > 1 || sum.y > 1 || sum.z > 1) ctx.status |= RTRB_ST_COLOR_GT_1;
-        }
-        RTRB_COUNT(ctx, RTRB_CNT_HIGHLIGHT);
-        if (is_first) *primary_hit = -2;
-        return;
-      }
-    }
-
-    // ---- World#intersect ----
-    HitRec bh; bh.p = mk(0, 0, 0); bh.dir_in = false;
-    if constexpr (BOX) bh.face = 0;
-    const int best_i = closest_hit_fast<BVH, BOX, KT>(P, o, d, r, bh, ctx, is_first);
-    if (best_i < 0) return;
-    if (is_first) *primary_hit = best_i;
-    RTRB_COUNT(ctx, RTRB_CNT_HITS);
-
+    (void)o;
     const DevGeom g = P.geom[best_i];
     const DevMat& M = P.mat[best_i];
     d3 n, delta;
@@ -858,6 +870,15 @@ __device__ __forceinline__ void process_item_fast(const FrameParams& P, const St
   }
 }
 
+template <int MAXS, bool BVH, bool BOX>
+__device__ __forceinline__ void process_item_fast(const FrameParams& P, const StackItem& it, StackItem* stack, int& sp,
+                                                  d3& sum, ThreadCtx& ctx, uint32_t pixel, uint32_t sample,
+                                                  bool is_first, int* primary_hit) {
+  HitRec bh;
+  const int best_i = item_phase_a<MAXS, BVH, BOX>(P, it, sum, ctx, is_first, primary_hit, bh);
+  if (best_i >= 0) item_phase_b<MAXS, BVH, BOX>(P, it, best_i, bh, stack, sp, sum, ctx, pixel, sample);
+}
+
 // RayTracer#trace_sync for one sample (non-persistent form; used by tools and kept for reference).
 template <int MAXS, bool BVH, bool BOX>
 __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
@@ -900,8 +921,14 @@ __device__ __forceinline__ d3 trace_sample_fast_lockstep(const FrameParams& P, d
   *primary_hit = -1;
   if (active) ctx.max_stack = max(ctx.max_stack, 1u);
   while (__syncthreads_or(have ? 1 : 0)) {
+    HitRec bh;
+    int best_i = -1;
+    if (have) best_i = item_phase_a<MAXS, BVH, BOX>(P, it, sum, ctx, first, primary_hit, bh);
+    // phase boundary: with the BVH filter the whole CTA also moves from intersection to shading together (config 5:
+    // 4.22 -> 3.82 ms); with the linear filter the second barrier costs more than it saves (config 3: +3 %)
+    if constexpr (BVH) __syncthreads();
     if (have) {
-      process_item_fast<MAXS, BVH, BOX>(P, it, stack, sp, sum, ctx, pixel, sample, first, primary_hit);
+      if (best_i >= 0) item_phase_b<MAXS, BVH, BOX>(P, it, best_i, bh, stack, sp, sum, ctx, pixel, sample);
       first = false;
       if (sp == 0) have = false;
       else {
