@@ -48,45 +48,66 @@ static double ivar_f(VALUE obj, const char* name, const char* what) {
 }
 static int is_a(VALUE obj, const char* klass_path) { return RTEST(rb_obj_is_kind_of(obj, rb_path2class(klass_path))); }
 
-/* Texture -> 8-bit RGB rows: Texture#to_a holds rows of Vec3(v8/256.0) (texture.rb:12-20,34-36) */
-static uint8_t* texture_bytes(VALUE tex, int* w, int* h) {
-  *w = NUM2INT(rb_funcall(tex, rb_intern("width"), 0));
-  *h = NUM2INT(rb_funcall(tex, rb_intern("height"), 0));
+/* Texture -> 8-bit RGB rows: Texture#to_a holds rows of Vec3(v8/256.0) (texture.rb:12-20,34-36).  The buffer is
+ * entered into `td` BEFORE it is filled, so the rb_ensure cleanup frees it even when a texel conversion raises. */
+static void texture_bytes(VALUE tex, rtrb_texture_desc* td) {
+  const int w = NUM2INT(rb_funcall(tex, rb_intern("width"), 0));
+  const int h = NUM2INT(rb_funcall(tex, rb_intern("height"), 0));
   VALUE rows = rb_funcall(tex, rb_intern("to_a"), 0);
-  uint8_t* px = (uint8_t*)malloc((size_t)(*w) * (*h) * 3);
-  for (int y = 0; y < *h; ++y) {
+  uint8_t* px = (uint8_t*)malloc((size_t)w * h * 3);
+  if (!px) rb_raise(rb_eNoMemError, "rtrb_b200: texture buffer");
+  td->rgb8 = px; td->width = w; td->height = h;
+  for (int y = 0; y < h; ++y) {
     VALUE row = rb_ary_entry(rows, y);
-    for (int x = 0; x < *w; ++x) {
+    for (int x = 0; x < w; ++x) {
       double c[3];
       vec3_into(rb_ary_entry(row, x), c, "texel");
-      for (int k = 0; k < 3; ++k) px[((size_t)y * (*w) + x) * 3 + k] = (uint8_t)(c[k] * 256.0 + 0.5);
+      for (int k = 0; k < 3; ++k) px[((size_t)y * w + x) * 3 + k] = (uint8_t)(c[k] * 256.0 + 0.5);
     }
   }
-  return px;
 }
 
-static VALUE renderer_initialize(VALUE self, VALUE world) {
+/* Flattening World -> rtrb_scene_desc can raise half way (a nil ivar, a non-numeric value: vec3_into / ivar_f call
+ * rb_raise).  The scratch arrays therefore live in a struct that rb_ensure frees whether the body returns or raises. */
+typedef struct {
+  VALUE self, world;
+  rtrb_object_desc* od;
+  rtrb_light_desc* ld;
+  rtrb_texture_desc* td;
+  int n_tex;
+} init_call;
+
+static VALUE init_cleanup(VALUE p) {
+  init_call* c = (init_call*)p;
+  for (int i = 0; i < c->n_tex; ++i) free((void*)c->td[i].rgb8);
+  free(c->od); free(c->ld); free(c->td);
+  return Qnil;
+}
+
+static VALUE init_body(VALUE p) {
+  init_call* c = (init_call*)p;
+  VALUE world = c->world;
   VALUE objs = ivar(world, "@world_objects"), lights = ivar(world, "@lights");
   long n_obj = RARRAY_LEN(objs), n_li = RARRAY_LEN(lights);
-  rtrb_object_desc* od = (rtrb_object_desc*)calloc(n_obj > 0 ? n_obj : 1, sizeof(*od));
-  rtrb_light_desc* ld = (rtrb_light_desc*)calloc(n_li > 0 ? n_li : 1, sizeof(*ld));
-  rtrb_texture_desc* td = (rtrb_texture_desc*)calloc(n_obj > 0 ? n_obj : 1, sizeof(*td));
-  int n_tex = 0;
+  rtrb_object_desc* od = c->od = (rtrb_object_desc*)calloc(n_obj > 0 ? n_obj : 1, sizeof(*od));
+  rtrb_light_desc* ld = c->ld = (rtrb_light_desc*)calloc(n_li > 0 ? n_li : 1, sizeof(*ld));
+  rtrb_texture_desc* td = c->td = (rtrb_texture_desc*)calloc(n_obj > 0 ? n_obj : 1, sizeof(*td));
+  if (!od || !ld || !td) rb_raise(rb_eNoMemError, "rtrb_b200: scene scratch");
   for (long i = 0; i < n_obj; ++i) {
     VALUE o = rb_ary_entry(objs, i);
     rtrb_object_desc* d = &od[i];
     d->texture = -1;
     VALUE tex = ivar(o, "@texture");
     if (!NIL_P(tex)) {
-      int w, h;
-      td[n_tex].rgb8 = texture_bytes(tex, &w, &h);
-      td[n_tex].width = w; td[n_tex].height = h;
-      d->texture = n_tex++;
-      d->texture_horizontal_scale = ivar_f(o, "@texture_horizontal_scale", "texture_horizontal_scale");
-      d->texture_vertical_scale = ivar_f(o, "@texture_vertical_scale", "texture_vertical_scale");
-      VALUE uo = ivar(o, "@texture_u_offset"), vo = ivar(o, "@texture_v_offset");
-      d->texture_u_offset = NIL_P(uo) ? 0.0 : NUM2DBL(uo);   /* texture.rb:15-16 */
-      d->texture_v_offset = NIL_P(vo) ? 0.0 : NUM2DBL(vo);
+      d->texture = c->n_tex++;          /* counted first: init_cleanup then frees a half-filled buffer too */
+      texture_bytes(tex, &td[d->texture]);
+      /* what Texture#color really uses (texture.rb:9-10,15-16,24-25): the Texture object's own scales and offsets.
+       * Sphere passes its texture_u/v_offset on (sphere.rb:25); Plane and Box do not (plane.rb:35, box.rb:76), so
+       * their textures keep 0.0 whatever the YAML says. */
+      d->texture_horizontal_scale = ivar_f(tex, "@horizontal_scale", "texture horizontal_scale");
+      d->texture_vertical_scale = ivar_f(tex, "@vertical_scale", "texture vertical_scale");
+      d->texture_u_offset = ivar_f(tex, "@u_off", "texture u_off");
+      d->texture_v_offset = ivar_f(tex, "@v_off", "texture v_off");
     }
     if (is_a(o, "Alex::Objects::Sphere")) {
       d->type = RTRB_OBJ_SPHERE;
@@ -142,16 +163,21 @@ static VALUE renderer_initialize(VALUE self, VALUE world) {
   memset(&sd, 0, sizeof(sd));
   sd.max_distance = ivar_f(world, "@max_distance", "max_distance");
   sd.soft_shadow_exponent = ivar_f(world, "@soft_shadow_exponent", "soft_shadow_exponent");
-  sd.n_objects = (int32_t)n_obj; sd.n_lights = (int32_t)n_li; sd.n_textures = n_tex;
+  sd.n_objects = (int32_t)n_obj; sd.n_lights = (int32_t)n_li; sd.n_textures = c->n_tex;
   sd.objects = od; sd.lights = ld; sd.textures = td;
 
   shim_renderer* s;
-  Data_Get_Struct(self, shim_renderer, s);
+  Data_Get_Struct(c->self, shim_renderer, s);
   int rc = rtrb_renderer_create(&sd, 0, &s->r);
-  for (int i = 0; i < n_tex; ++i) free((void*)td[i].rgb8);
-  free(od); free(ld); free(td);
   if (rc != RTRB_OK) rb_raise(rb_eRuntimeError, "%s", rtrb_last_error());
-  return self;
+  return c->self;
+}
+
+static VALUE renderer_initialize(VALUE self, VALUE world) {
+  init_call c;
+  memset(&c, 0, sizeof(c));
+  c.self = self; c.world = world;
+  return rb_ensure(init_body, (VALUE)&c, init_cleanup, (VALUE)&c);
 }
 
 static VALUE renderer_alloc(VALUE klass) {

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RTRB_ABI_VERSION 2
+#define RTRB_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -156,8 +156,10 @@ typedef struct rtrb_render_opts {
   int32_t skip_outputs; /* rtrb_render_device only: RTRB_SKIP_RGB | RTRB_SKIP_HIT drop the optional float RGB
                            (24 B/pixel) / hit-id (4 B/pixel) frames; 0 keeps both for rtrb_download */
   void* stream;         /* cudaStream_t to launch on; NULL = the renderer's own stream */
-  void* rgba_device_out;/* device pointer (possibly a peer mapping) the 8-bit frame is written to;
-                           NULL = the renderer's own framebuffer */
+  void* rgba_device_out;/* rtrb_render_device / rtrb_submit only: device pointer (possibly a peer mapping) the 8-bit
+                           frame is written to; NULL = the renderer's own framebuffer.  The host-buffer calls
+                           (rtrb_render, rtrb_render_multi) reject it with RTRB_ERR_INVALID, and rtrb_download refuses
+                           to fetch an 8-bit frame that went elsewhere */
   int32_t pixel_format; /* RTRB_FMT_*: layout of the 8-bit frame (device buffer and host copies alike) */
   int32_t reserved0;
 } rtrb_render_opts;
@@ -220,18 +222,25 @@ int rtrb_render(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
  * device->host copy into rgba_host (pinned memory recommended) on a separate copy stream, then
  * returns; rtrb_wait blocks until that frame's bytes and stats are in host memory.  Up to four frames
  * may be in flight per renderer (tickets are consecutive integers; wait for them in order), so
- * later frames render while earlier ones cross PCIe.  8-bit frame only (opts->pixel_format). */
+ * later frames render while earlier ones cross PCIe.  8-bit frame only (opts->pixel_format).  rtrb_wait fails with
+ * RTRB_ERR_INVALID for a ticket that is not the one occupying its slot (stale or duplicate). */
 int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts, uint8_t* rgba_host,
                 int* ticket_out);
 int rtrb_wait(rtrb_renderer* r, int ticket, rtrb_stats* stats_out);
 
 /* -- multi-GPU tile gather without a collective ----------------------------------------------- */
-/* Device pointer of the renderer's RGBA8 framebuffer for (width,height) (allocates it if needed). */
+/* Device pointer of the renderer's RGBA8 framebuffer for (width,height) (allocates it if needed).  From this
+ * call (or rtrb_framebuffer_ipc_export) on the framebuffer is PINNED: a later frame or request that needs a larger
+ * one fails with RTRB_ERR_INVALID instead of reallocating memory that peers may still be writing to. */
 int rtrb_framebuffer_device_ptr(rtrb_renderer* r, int width, int height, void** ptr_out);
 /* Copies width*height*4 bytes of that framebuffer to host memory (blocking).  With a framebuffer
  * allocated for (width, height * n) this fetches n frames that were rendered into consecutive slots
  * through rgba_device_out. */
 int rtrb_framebuffer_download(rtrb_renderer* r, int width, int height, uint8_t* rgba_host);
+/* Queues a copy of the first `bytes` bytes of that framebuffer to host memory on `stream` (NULL = the renderer's own)
+ * and returns without synchronising: the last step of a multi-process tile gather, ordered on the caller's stream
+ * behind whatever tells rank 0 that every rank's tiles have landed (render_fork's parent, camera.rb:42-52). */
+int rtrb_framebuffer_copy_async(rtrb_renderer* r, size_t bytes, uint8_t* host, void* stream);
 /* CUDA IPC handle (64 bytes) of that framebuffer, to hand to the other per-GPU processes. */
 int rtrb_framebuffer_ipc_export(rtrb_renderer* r, int width, int height, uint8_t handle_out[64]);
 /* Maps a peer process's framebuffer into this process; pass the result as rgba_device_out. */

@@ -2,7 +2,7 @@
 for field; tests/test_abi.py checks sizeof() against the values the compiled library reports."""
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 RTRB_OK, RTRB_ERR_INVALID, RTRB_ERR_CUDA, RTRB_ERR_RAISED, RTRB_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 

@@ -13,7 +13,7 @@ EXPORTS = (
     "rtrb_abi_version", "rtrb_last_error", "rtrb_device_count",
     "rtrb_renderer_create", "rtrb_renderer_destroy",
     "rtrb_render_device", "rtrb_download", "rtrb_render", "rtrb_submit", "rtrb_wait",
-    "rtrb_framebuffer_device_ptr", "rtrb_framebuffer_download", "rtrb_framebuffer_ipc_export", "rtrb_ipc_open", "rtrb_ipc_close",
+    "rtrb_framebuffer_device_ptr", "rtrb_framebuffer_download", "rtrb_framebuffer_copy_async", "rtrb_framebuffer_ipc_export", "rtrb_ipc_open", "rtrb_ipc_close",
     "rtrb_peer_push", "rtrb_peer_push_join",
     "rtrb_render_multi", "rtrb_tile_partition", "rtrb_measure_fma_peak", "rtrb_launch_count", "rtrb_last_mt_passes",
 )
@@ -50,6 +50,7 @@ def lib():
     L.rtrb_wait.argtypes = [C.c_void_p, C.c_int, P(_abi.Stats)]
     L.rtrb_framebuffer_device_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int, P(C.c_void_p)]
     L.rtrb_framebuffer_download.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.rtrb_framebuffer_copy_async.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.rtrb_framebuffer_ipc_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.rtrb_ipc_open.argtypes = [C.c_int, C.c_void_p, P(C.c_void_p)]
     L.rtrb_ipc_close.argtypes = [C.c_int, C.c_void_p]

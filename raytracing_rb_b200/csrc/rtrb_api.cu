@@ -135,6 +135,7 @@ struct FrameCtl {
   // facts of the frame in flight, needed to finish its stats later
   int W = 0, H = 0, S = 0, E = 0, n_tiles = 0;
   bool detail = false, in_flight = false, timed = false;
+  unsigned ticket = 0;              // the rtrb_submit ticket occupying this slot while in_flight
   size_t px_count = 0;
   int init() {
     cudaError_t e;
@@ -198,7 +199,7 @@ struct rtrb_renderer {
   DevBuf<double> lens_tab;             // [W + H] per-column / per-row retina offsets
   double lens_key[4] = {0, 0, 0, 0};   // (W, H, retina_width, retina_height) the table was built for
   int tiles_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
-  DevBuf<double> samples, extra_samples, rgb;
+  DevBuf<double> samples, extra_samples, pre_avg, rgb;
   DevBuf<uint32_t> extra_list;
   // RTRB_RNG_MT validation mode
   DevBuf<double> mt_stream;
@@ -210,10 +211,11 @@ struct rtrb_renderer {
   int mt_iterations = 0;               // iterations the last MT frame needed to reach its fixed point
   DevBuf<int32_t> hit;
   DevBuf<uint8_t> rgba;
+  bool fb_exported = false;            // its address / IPC handle has been handed out: it may no longer move
   int fb_w = 0, fb_h = 0;
   // last frame
   int last_w = 0, last_h = 0;
-  bool last_has_rgb = false, last_has_hit = false;
+  bool last_has_rgb = false, last_has_hit = false, last_rgba_own = true;
   int last_bpp = 4;
   cudaStream_t last_stream = nullptr;
   bool timing_valid = false;
@@ -272,7 +274,8 @@ __global__ void __launch_bounds__(256) resolve_extra_kernel(const __grid_constan
     int x, y;
     if (!slot_to_xy(P, slot, x, y)) continue;
     double ax, ay, az, variance;
-    pre_mean(P, slot, ax, ay, az, variance);
+    if (P.fuse_resolve == 2) { ax = P.pre_avg[(size_t)e * 3]; ay = P.pre_avg[(size_t)e * 3 + 1]; az = P.pre_avg[(size_t)e * 3 + 2]; }
+    else pre_mean(P, slot, ax, ay, az, variance);
     const double* s = P.extra_samples + (size_t)e * E * 3;
     double cx = 0.0, cy = 0.0, cz = 0.0;
     for (int j = 0; j < E; ++j) { cx += s[j * 3 + 0]; cy += s[j * 3 + 1]; cz += s[j * 3 + 2]; }
@@ -614,10 +617,17 @@ struct FrameTargets {  // where this renderer writes (own buffers, or rank 0's t
   bool no_fill = false;  // multi-GPU: the caller pre-fills, ranks must not race on the shared buffer
 };
 
-int ensure_framebuffers(rtrb_renderer* r, int w, int h, bool rgb, bool hit) {
+// Own framebuffers for a (w, h) frame.  `rgba` = false when the 8-bit frame goes to a caller-supplied device buffer
+// (rgba_device_out, a peer mapping, a pipeline slot).  Once the 8-bit framebuffer's address or IPC handle has been
+// handed out (rtrb_framebuffer_device_ptr / _ipc_export) it is pinned: peers may be storing into it, so a frame that
+// would need a larger one fails instead of freeing memory other ranks still write to.
+int ensure_framebuffers(rtrb_renderer* r, int w, int h, bool rgba, bool rgb, bool hit) {
   size_t px = (size_t)w * h;
   CUDA_TRY(cudaSetDevice(r->device));
-  if (r->rgba.n < px * 4) {
+  if (rgba && r->rgba.n < px * 4) {
+    if (r->fb_exported)
+      return fail(RTRB_ERR_INVALID, "the %dx%d frame needs a larger framebuffer than the one whose device pointer / IPC handle "
+                                    "was exported (%zu bytes); it cannot be reallocated while peers may write to it", w, h, r->rgba.n);
     CUDA_TRY(r->rgba.ensure(px * 4));
     CUDA_TRY(cudaMemset(r->rgba.p, 0, px * 4));
   }
@@ -675,11 +685,12 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
     tg.want_rgb = !(opts.skip_outputs & RTRB_SKIP_RGB);
     tg.want_hit = !(opts.skip_outputs & RTRB_SKIP_HIT);
   }
+  if (!tg.rgba && opts.rgba_device_out) tg.rgba = (uint8_t*)opts.rgba_device_out;
   {
-    int rc = ensure_framebuffers(r, W, H, tg.want_rgb && !tg.rgb, tg.want_hit && !tg.hit);
+    int rc = ensure_framebuffers(r, W, H, tg.rgba == nullptr, tg.want_rgb && !tg.rgb, tg.want_hit && !tg.hit);
     if (rc) return rc;
   }
-  if (!tg.rgba) tg.rgba = opts.rgba_device_out ? (uint8_t*)opts.rgba_device_out : r->rgba.p;
+  if (!tg.rgba) tg.rgba = r->rgba.p;
   if (tg.want_rgb && !tg.rgb) tg.rgb = r->rgb.p;
   if (tg.want_hit && !tg.hit) tg.hit = r->hit.p;
   if (!tg.want_rgb) tg.rgb = nullptr;
@@ -736,11 +747,21 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   const size_t n_slots = (size_t)n_tiles * RTRB_SUPER_PIXELS;
   const int S = cam->pre_sample_times;
   const int E = cam->max_sample_times > S ? cam->max_sample_times - S : 0;
-  if (n_slots * (size_t)S * 3 * sizeof(double) > ((size_t)96 << 30) || n_slots * (size_t)E * 3 * sizeof(double) > ((size_t)64 << 30))
+  // Who finishes render_at (FrameParams::fuse_resolve).  The FAST64 ray-tree kernels resolve a pixel inside the CTA
+  // that traced its samples whenever the sample count divides the CTA size: no FP64 sample buffer (24 B per sample:
+  // 12.7 GB for one 4K / 64 spp frame) and no resolve launch.
+  const bool strict_mode = opts.precision == RTRB_PREC_STRICT;
+  int fuse = (S == 1 && cam->variant_threshold > 0) ? 1 : 0;
+#ifndef RTRB_NO_FUSE2  // (build-time A/B switch, profiles/README.md)
+  if (!strict_mode && !mt_mode && cam->trace_depth > 1 && S <= RTRB_TREE_MIN_BLOCK && RTRB_TREE_MIN_BLOCK % S == 0) fuse = 2;
+#endif
+  const bool need_samples = fuse == 0;
+  if ((need_samples && n_slots * (size_t)S * 3 * sizeof(double) > ((size_t)96 << 30)) || n_slots * (size_t)E * 3 * sizeof(double) > ((size_t)64 << 30))
     return fail(RTRB_ERR_UNSUPPORTED, "sample buffer would exceed the per-frame memory budget");
-  CUDA_TRY(r->samples.ensure(std::max<size_t>(1, n_slots * S * 3)));
+  if (need_samples) CUDA_TRY(r->samples.ensure(std::max<size_t>(1, n_slots * S * 3)));
   CUDA_TRY(r->extra_list.ensure(std::max<size_t>(1, n_slots)));
   if (E > 0) CUDA_TRY(r->extra_samples.ensure(n_slots * E * 3));
+  if (E > 0 && fuse == 2) CUDA_TRY(r->pre_avg.ensure(n_slots * 3));
   FrameCtl& fc = ctl ? *ctl : r->main_ctl;
 
   FrameParams P;
@@ -777,7 +798,8 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.x0 = x0; P.y0 = y0; P.x1 = x1; P.y1 = y1;
   P.n_tiles = n_tiles; P.stx_count = stx_count; P.tiles = r->tiles.p;
   P.lens_sx = r->lens_tab.p; P.lens_sy = r->lens_tab.p + W;
-  P.samples = r->samples.p; P.rgb = tg.rgb; P.hit = tg.hit; P.rgba = tg.rgba;
+  P.samples = need_samples ? r->samples.p : nullptr; P.rgb = tg.rgb; P.hit = tg.hit; P.rgba = tg.rgba;
+  P.pre_avg = r->pre_avg.p;
   P.counters = fc.d.p; P.first_bad = fc.d.p + RTRB_CNT_N;
   P.work_counter = fc.d.p + RTRB_CNT_N + 1;
   P.status = reinterpret_cast<uint32_t*>(fc.d.p + RTRB_CNT_N + 3);
@@ -788,10 +810,10 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   // the Box code lives only in the full-counter kernel variants (rtrb_trace.cuh, trace_dispatch)
   P.count_detail = (opts.count_detail || r->n_boxes > 0) ? 1 : 0;
   P.pixel_format = opts.pixel_format;
-  // a single sample with a positive threshold can never take the adaptive branch (variance == 0)
-  P.fuse_resolve = (S == 1 && cam->variant_threshold > 0) ? 1 : 0;
+  // (1: a single sample with a positive threshold can never take the adaptive branch, variance == 0)
+  P.fuse_resolve = fuse;
 
-  const bool strict = opts.precision == RTRB_PREC_STRICT;
+  const bool strict = strict_mode;
   // timing events only for the blocking calls that return stats: a timestamp between two kernels keeps
   // frame i+1 from starting under frame i's tail, so pipelined frames (rtrb_submit) are not timed and
   // report device_ms = trace_ms = 0
@@ -872,7 +894,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
       CUDA_TRY(cudaGetLastError());
       g_launches++;
     }
-    if (E > 0 && !P.fuse_resolve) {
+    if (E > 0 && P.fuse_resolve != 1) {
       CUDA_TRY(strict ? rtrb_launch_trace_extra_strict(P, stack_need, stream) : rtrb_launch_trace_extra_fast(P, stack_need, stream));
       g_launches++;
       resolve_extra_kernel<<<296, 256, 0, stream>>>(P);
@@ -882,6 +904,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   }
   CUDA_TRY(cudaEventRecord(fc.ev1, stream));
   r->last_w = W; r->last_h = H;
+  r->last_rgba_own = tg.rgba == r->rgba.p;
   r->last_has_rgb = tg.rgb == r->rgb.p && tg.rgb != nullptr;
   r->last_has_hit = tg.hit == r->hit.p && tg.hit != nullptr;
   r->last_stream = stream;
@@ -1006,7 +1029,7 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   r->geom.release(); r->mat.release(); r->lights.release(); r->lens_tab.release(); r->boxes.release();
   r->bvh.release(); r->light_tab.release();
   r->cull_sph.release(); r->cull_pl.release(); r->sph_index.release(); r->pl_index.release(); r->lights_f.release(); r->tiles.release(); r->samples.release();
-  r->extra_samples.release(); r->rgb.release(); r->extra_list.release(); r->hit.release(); r->rgba.release();
+  r->extra_samples.release(); r->pre_avg.release(); r->rgb.release(); r->extra_list.release(); r->hit.release(); r->rgba.release();
   r->main_ctl.destroy();
   for (int i = 0; i < RTRB_PIPE_SLOTS; ++i) r->pipe_ctl[i].destroy();
   for (uint8_t* t : r->textures) cudaFree(t);
@@ -1030,7 +1053,10 @@ int rtrb_download(rtrb_renderer* r, uint8_t* rgba, double* rgb_or_null, int32_t*
   CUDA_TRY(cudaSetDevice(r->device));
   cudaStream_t s = r->last_stream ? r->last_stream : r->stream;
   size_t px = (size_t)r->last_w * r->last_h;
-  if (rgba) CUDA_TRY(cudaMemcpyAsync(rgba, r->rgba.p, px * (size_t)r->last_bpp, cudaMemcpyDeviceToHost, s));
+  if (rgba) {
+    if (!r->last_rgba_own) return fail(RTRB_ERR_INVALID, "the last frame was written to rgba_device_out, not to the renderer's framebuffer");
+    CUDA_TRY(cudaMemcpyAsync(rgba, r->rgba.p, px * (size_t)r->last_bpp, cudaMemcpyDeviceToHost, s));
+  }
   if (rgb_or_null) {
     if (!r->last_has_rgb) return fail(RTRB_ERR_INVALID, "the last frame kept no float RGB");
     CUDA_TRY(cudaMemcpyAsync(rgb_or_null, r->rgb.p, px * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1046,6 +1072,8 @@ int rtrb_download(rtrb_renderer* r, uint8_t* rgba, double* rgb_or_null, int32_t*
 int rtrb_render(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts, uint8_t* rgba,
                 double* rgb_or_null, int32_t* hit_or_null, rtrb_stats* stats_out) {
   if (!rgba) return fail(RTRB_ERR_INVALID, "rgba is NULL");
+  if (opts && opts->rgba_device_out)
+    return fail(RTRB_ERR_INVALID, "rgba_device_out does not combine with a host-buffer call (use rtrb_render_device)");
   FrameTargets tg;
   tg.want_rgb = rgb_or_null != nullptr;
   tg.want_hit = hit_or_null != nullptr;
@@ -1102,6 +1130,7 @@ int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   CUDA_TRY(cudaEventRecord(fc.ctl_copied, r->ctl_stream));
   // (the slot is reused only after rtrb_wait has host-synchronised on `copied`, so no stream wait is needed)
   fc.in_flight = true;
+  fc.ticket = ticket;
   r->next_ticket = ticket + 1;
   *ticket_out = (int)ticket;
   return RTRB_OK;
@@ -1110,7 +1139,7 @@ int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
 int rtrb_wait(rtrb_renderer* r, int ticket, rtrb_stats* stats_out) {
   if (!r || !r->pipe_ready) return fail(RTRB_ERR_INVALID, "nothing submitted");
   FrameCtl& fc = r->pipe_ctl[(unsigned)ticket % RTRB_PIPE_SLOTS];
-  if (!fc.in_flight) return fail(RTRB_ERR_INVALID, "ticket %d is not in flight", ticket);
+  if (!fc.in_flight || fc.ticket != (unsigned)ticket) return fail(RTRB_ERR_INVALID, "ticket %d is not in flight", ticket);
   CUDA_TRY(cudaSetDevice(r->device));
   CUDA_TRY(cudaEventSynchronize(fc.copied));
   CUDA_TRY(cudaEventSynchronize(fc.ctl_copied));
@@ -1121,8 +1150,9 @@ int rtrb_wait(rtrb_renderer* r, int ticket, rtrb_stats* stats_out) {
 
 int rtrb_framebuffer_device_ptr(rtrb_renderer* r, int width, int height, void** ptr_out) {
   if (!r || !ptr_out || width <= 0 || height <= 0) return fail(RTRB_ERR_INVALID, "bad argument");
-  int rc = ensure_framebuffers(r, width, height, false, false);
+  int rc = ensure_framebuffers(r, width, height, true, false, false);
   if (rc) return rc;
+  r->fb_exported = true;
   *ptr_out = r->rgba.p;
   return RTRB_OK;
 }
@@ -1137,10 +1167,20 @@ int rtrb_framebuffer_download(rtrb_renderer* r, int width, int height, uint8_t* 
   return RTRB_OK;
 }
 
+int rtrb_framebuffer_copy_async(rtrb_renderer* r, size_t bytes, uint8_t* host, void* stream) {
+  if (!r || !host) return fail(RTRB_ERR_INVALID, "bad argument");
+  if (bytes == 0) return RTRB_OK;
+  CUDA_TRY(cudaSetDevice(r->device));
+  if (r->rgba.n < bytes) return fail(RTRB_ERR_INVALID, "framebuffer is smaller than %zu bytes", bytes);
+  CUDA_TRY(cudaMemcpyAsync(host, r->rgba.p, bytes, cudaMemcpyDeviceToHost, stream ? (cudaStream_t)stream : r->stream));
+  return RTRB_OK;
+}
+
 int rtrb_framebuffer_ipc_export(rtrb_renderer* r, int width, int height, uint8_t handle_out[64]) {
   if (!r || !handle_out) return fail(RTRB_ERR_INVALID, "bad argument");
-  int rc = ensure_framebuffers(r, width, height, false, false);
+  int rc = ensure_framebuffers(r, width, height, true, false, false);
   if (rc) return rc;
+  r->fb_exported = true;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   cudaIpcMemHandle_t h;
   CUDA_TRY(cudaIpcGetMemHandle(&h, r->rgba.p));
@@ -1186,10 +1226,12 @@ int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_
                       const rtrb_render_opts* opts_in, uint8_t* rgba, double* rgb_or_null, int32_t* hit_or_null,
                       rtrb_stats* stats_out) {
   if (!renderers || n < 1 || !cam || !rgba) return fail(RTRB_ERR_INVALID, "bad argument");
+  if (opts_in && opts_in->rgba_device_out)
+    return fail(RTRB_ERR_INVALID, "rgba_device_out does not combine with a host-buffer call (use rtrb_render_device)");
   if (n == 1) return rtrb_render(renderers[0], cam, opts_in, rgba, rgb_or_null, hit_or_null, stats_out);
   rtrb_renderer* root = renderers[0];
   const bool want_rgb = rgb_or_null != nullptr, want_hit = hit_or_null != nullptr;
-  int rc = ensure_framebuffers(root, cam->width, cam->height, want_rgb, want_hit);
+  int rc = ensure_framebuffers(root, cam->width, cam->height, true, want_rgb, want_hit);
   if (rc) return rc;
   // peer access root <- others (writes land in root's framebuffer over NVLink; no collective)
   for (int i = 1; i < n; ++i) {
@@ -1262,7 +1304,7 @@ int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_
   }
   if (stats_out) *stats_out = agg;
   root->last_w = cam->width; root->last_h = cam->height;
-  root->last_has_rgb = want_rgb; root->last_has_hit = want_hit;
+  root->last_has_rgb = want_rgb; root->last_has_hit = want_hit; root->last_rgba_own = true;
   root->last_stream = root->stream;
   root->last_bpp = base.pixel_format == RTRB_FMT_RGB8 ? 3 : 4;
   std::string keep = g_last_error;

@@ -1,7 +1,8 @@
 // rtrb_launch.h — host-callable launchers of the trace kernels.  Each arithmetic mode lives in its
-// own translation unit because FMA contraction is a per-TU compiler flag:
-//   rtrb_trace_strict.cu  (-fmad=false)  RTRB_PREC_STRICT
-//   rtrb_trace_fast.cu    (-fmad=true)   RTRB_PREC_FAST64
+// own translation units, all compiled -fmad=false (the exact FP64 parts must round like the reference's scalar code;
+// the FP32 filter of FAST64 uses explicit fmaf()):
+//   rtrb_trace_strict.cu                          RTRB_PREC_STRICT
+//   rtrb_trace_fast.cu + rtrb_trace_fast_*.cu     RTRB_PREC_FAST64 (dispatch + one TU per work-stack capacity)
 #pragma once
 #include <cuda_runtime.h>
 

@@ -600,16 +600,27 @@ __device__ __forceinline__ bool decode_pixel(const FrameParams& P, uint32_t slot
   return x >= P.x0 && x < P.x1 && y >= P.y0 && y < P.y1;
 }
 
+// Records a pixel whose sample set a status bit (the reference would have raised there): status word and the
+// first offending pixel in the reference's pixel order (x outer, y inner).  Clears ctx.status so that a thread
+// which goes on to other pixels (grid-stride / persistent loops) attributes later bits to the right pixel.
+__device__ __forceinline__ void report_status(const FrameParams& P, ThreadCtx& ctx, int x, int y) {
+  if (ctx.status) {
+    atomicOr(&P.status[0], ctx.status);
+    // smallest x*H + y wins; stored complemented (atomicMax) so the control block can be zero-initialised
+    atomicMax(P.first_bad, ~((unsigned long long)x * (unsigned long long)P.height + (unsigned long long)y));
+    ctx.status = 0;
+  }
+}
+
 __device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, int x, int y, bool active) {
-  // warp totals by hardware reduction (REDUX), block totals through shared memory, then ONE atomic
-  // per block and counter: 65 K warps hammering three addresses would serialise in the L2 atomic unit
+  // warp totals by hardware reduction (REDUX), then one fire-and-forget RED per warp and counter, spread over
+  // RTRB_HOT_SLICES address pairs (the host sums the slices): no block barrier, and no single L2 line taking
+  // 65 K atomics per frame
   const unsigned full = 0xffffffffu;
   const uint32_t rays = __reduce_add_sync(full, ctx.rays), shadow = __reduce_add_sync(full, ctx.shadow),
                  ms = __reduce_max_sync(full, ctx.max_stack);
   const int lane = threadIdx.x & 31;
   if (lane == 0) {
-    // one fire-and-forget RED per warp and counter, spread over RTRB_HOT_SLICES address pairs (the host
-    // sums the slices): no block barrier, and no single L2 line taking 65 K atomics per frame
     unsigned long long* hot = P.hot + 2u * ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (RTRB_HOT_SLICES - 1));
     if (rays) atomicAdd(&hot[0], (unsigned long long)rays);
     if (shadow) atomicAdd(&hot[1], (unsigned long long)shadow);
@@ -623,11 +634,7 @@ __device__ __forceinline__ void flush_ctx(const FrameParams& P, ThreadCtx& ctx, 
       if (lane == 0 && v) atomicAdd(&P.counters[i], (unsigned long long)v);
     }
   }
-  if (active && ctx.status) {
-    atomicOr(&P.status[0], ctx.status);
-    // smallest x*H + y wins; stored complemented (atomicMax) so the control block can be zero-initialised
-    atomicMax(P.first_bad, ~((unsigned long long)x * (unsigned long long)P.height + (unsigned long long)y));
-  }
+  if (active) report_status(P, ctx, x, y);
 }
 
 __device__ __forceinline__ void init_ctx(ThreadCtx& ctx, bool detail) {
@@ -654,20 +661,6 @@ template <int MAXS, bool BVH, bool BOX>
 __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
                                                 ThreadCtx& ctx, int* primary_hit);
 
-// FAST64 ray-tree kernels process their work items in LOCKSTEP: one block barrier per item keeps the CTA's warps in
-// the same code at the same time.  These kernels are ~150 KB of SASS and were bound by instruction fetch (ncu:
-// `no_instruction` 3.3 - 13.5 stall cycles per issued instruction); in lockstep the warps share what the instruction
-// caches hold.  Measured: config 3 4.02 -> 3.52 ms, config 4 4.76 -> 3.57 ms, config 5 5.68 -> 4.24 ms (4 spp) and
-// 25.1 -> 19.8 ms (64 spp).  -DRTRB_NO_LOCKSTEP restores the free-running loop.
-#ifndef RTRB_NO_LOCKSTEP
-#define RTRB_LOCKSTEP 1
-#endif
-#ifdef RTRB_LOCKSTEP
-template <int MAXS, bool BVH, bool BOX>
-__device__ __forceinline__ d3 trace_sample_fast_lockstep(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
-                                                         ThreadCtx& ctx, int* primary_hit, bool active);
-#endif
-
 // MODE: 0 = STRICT, 1 = FAST64 with the linear filter, 2 = FAST64 with the sphere BVH.
 // BOX: the FAST64 kernels carry the Box code only in their full-counter (DETAIL) variants; scenes with a
 // box are always dispatched there (rtrb_api.cu), so the lean hot kernels stay sphere/plane-only.
@@ -689,38 +682,6 @@ __device__ __forceinline__ void trace_pre_body(const FrameParams& P) {
   init_ctx(ctx, DETAIL);
   int x = 0, y = 0;
   bool active = false;
-#ifdef RTRB_LOCKSTEP
-  if constexpr (MODE >= 1 && MAXS > 1) {
-    // every thread of the CTA enters the item loop (threads without a sample only take part in its barriers)
-    uint32_t slot = 0, j = 0, pixel = 0;
-    d3 ro = mk(0, 0, 0), rd = mk(1, 0, 0);
-    if (w < total) {
-      if (S == 1u) { slot = (uint32_t)w; j = 0u; }
-      else { slot = (uint32_t)(w / S); j = (uint32_t)(w - (unsigned long long)slot * S); }
-      active = decode_pixel(P, slot, x, y);
-      if (active) {
-        pixel = (uint32_t)y * (uint32_t)P.width + (uint32_t)x;
-        double theta = 0.0;
-        if (P.aperture_radius != 0.0) {
-          uint32_t c0 = pixel, c1 = j, c2 = 0u, c3 = 0u;
-          philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
-          theta = res53(c0, c1);
-        }
-        lens_ray(P, x, y, theta, ro, rd);
-      }
-    }
-    int ph = -1;
-    d3 col = trace_sample_fast_lockstep<MAXS, MODE == 2, DETAIL>(P, ro, rd, pixel, j, ctx, &ph, active);
-    if (active) {
-      RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
-      if (P.fuse_resolve) write_pixel(P, x, y, col.x, col.y, col.z);
-      else { double* out = P.samples + w * 3ull; out[0] = col.x; out[1] = col.y; out[2] = col.z; }
-      if (j == 0 && P.hit) P.hit[(size_t)y * P.width + x] = ph;
-    }
-    flush_ctx(P, ctx, x, y, active);
-    return;
-  }
-#endif
   if (w < total) {
     uint32_t slot, j;
     if (S == 1u) { slot = (uint32_t)w; j = 0u; }
@@ -782,15 +743,14 @@ __device__ __forceinline__ void trace_extra_body(const FrameParams& P) {
     RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
     double* out = P.extra_samples + w * 3ull;
     out[0] = col.x; out[1] = col.y; out[2] = col.z;
+    report_status(P, ctx, x, y);  // this pixel's bits, before the loop moves to another pixel
   }
   flush_ctx(P, ctx, x, y, any);
 }
 
-// mean of the pre samples in order, then the variance test (camera.rb:72-87)
-__device__ __forceinline__ void pre_mean(const FrameParams& P, uint32_t slot, double& ax, double& ay, double& az,
-                                         double& variance) {
-  const int S = P.pre;
-  const double* s = P.samples + (size_t)slot * S * 3;
+// mean of the pre samples in order, then the variance test (camera.rb:72-87); `s` = the pixel's S sample colours
+__device__ __forceinline__ void pre_mean_of(const double* s, const int S, double& ax, double& ay, double& az,
+                                            double& variance) {
   ax = 0.0; ay = 0.0; az = 0.0;
   for (int j = 0; j < S; ++j) { ax += s[j * 3 + 0]; ay += s[j * 3 + 1]; az += s[j * 3 + 2]; }
   ax = ax / (double)S; ay = ay / (double)S; az = az / (double)S;
@@ -801,6 +761,10 @@ __device__ __forceinline__ void pre_mean(const FrameParams& P, uint32_t slot, do
     variance += m * m;
   }
   variance /= (double)S;
+}
+__device__ __forceinline__ void pre_mean(const FrameParams& P, uint32_t slot, double& ax, double& ay, double& az,
+                                         double& variance) {
+  pre_mean_of(P.samples + (size_t)slot * P.pre * 3, P.pre, ax, ay, az, variance);
 }
 
 // RTRB_RNG_MT: Camera#render_at (camera.rb:70-99) for ONE pixel in ONE thread, because the reference's

@@ -905,7 +905,20 @@ __device__ __forceinline__ d3 trace_sample_fast(const FrameParams& P, d3 ro, d3 
   return sum;
 }
 
-#ifdef RTRB_LOCKSTEP
+// ---- ray-tree kernels (trace_depth > 1): lockstep item loop + render_at finished inside the CTA ----------------
+//
+// One thread per (pixel, sample), 512-thread CTAs.  LOCKSTEP: every thread of the CTA takes part in one block barrier
+// per work item, so the CTA's warps execute the same phase of rt_map at the same time and share what the instruction
+// caches hold (these kernels are ~150 KB of SASS; free-running, `no_instruction` was the top stall at 3.3 - 13.5
+// cycles per issued instruction; profiles/README.md has the measurements, including the persistent warp-refill
+// variant that was tried in round 2 and rejected: mixing tree depths inside a CTA makes every round as slow as its
+// slowest item kind, config 3 3.5 -> 5.0 ms).
+//
+// IN-CTA RESOLVE: when the CTA holds every sample of its pixels (pre_sample_times divides the CTA size), the sample
+// colours go to shared memory after the loop and one thread per pixel finishes render_at (camera.rb:79-98): ordered
+// mean, variance of the signed maximum, adaptive decision, quantisation.  No per-sample FP64 buffer crosses HBM
+// (24 B per sample: 12.7 GB for one 4K / 64 spp frame) and no resolve kernel runs.  FrameParams::fuse_resolve == 2
+// selects it; other sample counts (3, 10, ...) write the sample buffer for resolve_kernel as before.
 template <int MAXS, bool BVH, bool BOX>
 __device__ __forceinline__ d3 trace_sample_fast_lockstep(const FrameParams& P, d3 ro, d3 rd, uint32_t pixel, uint32_t sample,
                                                          ThreadCtx& ctx, int* primary_hit, bool active) {
@@ -939,6 +952,83 @@ __device__ __forceinline__ d3 trace_sample_fast_lockstep(const FrameParams& P, d
   }
   return sum;
 }
-#endif
+
+// Kernel body: the first loop of render_at (camera.rb:73-78) for the CTA's samples, then (fuse_resolve == 2) its tail.
+template <int MAXS, bool BVH, bool DETAIL>
+__device__ __forceinline__ void trace_pre_tree_body(const FrameParams& P) {
+  extern __shared__ double rtrb_cta_samples[];  // [blockDim.x][3] when fuse_resolve == 2
+  const uint32_t S = (uint32_t)P.pre;
+  const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long total = (unsigned long long)P.n_tiles * RTRB_SUPER_PIXELS * S;
+  ThreadCtx ctx;
+  init_ctx(ctx, DETAIL);
+  int x = 0, y = 0;
+  bool active = false;
+  // every thread of the CTA enters the item loop (threads without a sample only take part in its barriers)
+  uint32_t slot = 0, j = 0, pixel = 0;
+  d3 ro = mk(0, 0, 0), rd = mk(1, 0, 0);
+  if (w < total) {
+    if (S == 1u) { slot = (uint32_t)w; j = 0u; }
+    else { slot = (uint32_t)(w / S); j = (uint32_t)(w - (unsigned long long)slot * S); }
+    active = decode_pixel(P, slot, x, y);
+    if (active) {
+      pixel = (uint32_t)y * (uint32_t)P.width + (uint32_t)x;
+      double theta = 0.0;
+      if (P.aperture_radius != 0.0) {
+        uint32_t c0 = pixel, c1 = j, c2 = 0u, c3 = 0u;
+        philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
+        theta = res53(c0, c1);  // Random.rand, camera.rb:135
+      }
+      lens_ray(P, x, y, theta, ro, rd);
+    }
+  }
+  int ph = -1;
+  const d3 col = trace_sample_fast_lockstep<MAXS, BVH, DETAIL>(P, ro, rd, pixel, j, ctx, &ph, active);
+  if (active) {
+    RTRB_COUNT(ctx, RTRB_CNT_SAMPLES);
+    if (j == 0 && P.hit) P.hit[(size_t)y * P.width + x] = ph;
+  }
+  if (P.fuse_resolve == 2) {
+    // S divides blockDim.x, so the S samples of a pixel are S consecutive threads of this CTA
+    double* mine = rtrb_cta_samples + (size_t)threadIdx.x * 3u;
+    mine[0] = col.x; mine[1] = col.y; mine[2] = col.z;
+    __syncthreads();
+    const bool resolver = active && j == 0u;
+    double ax = 0, ay = 0, az = 0, variance = 0;
+    if (resolver) pre_mean_of(mine, (int)S, ax, ay, az, variance);
+    const bool adaptive = resolver && variance >= P.variant_threshold;
+    // pixels that take the extra-sample branch (camera.rb:87-93): one ballot per warp, list positions by prefix
+    // popcount, one atomic per warp and counter
+    const unsigned amask = __ballot_sync(0xffffffffu, adaptive);
+    bool queued = false;
+    if (amask != 0u) {
+      const int lane = threadIdx.x & 31, leader = __ffs(amask) - 1;
+      uint32_t base = 0;
+      if (lane == leader) {
+        const uint32_t n = __popc(amask);
+        atomicAdd(&P.counters[RTRB_CNT_ADAPTIVE], (unsigned long long)n);
+        if (P.max_samples > P.pre) base = atomicAdd(P.extra_count, n);
+      }
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (adaptive) {
+        if (P.max_samples > P.pre) {
+          const uint32_t e = base + __popc(amask & ((1u << lane) - 1u));
+          P.extra_list[e] = slot;
+          double* m = P.pre_avg + (size_t)e * 3u;
+          m[0] = ax; m[1] = ay; m[2] = az;
+          queued = true;  // finished by resolve_extra_kernel
+        } else {  // empty extra loop: (average * pre + 0) / max  (camera.rb:93)
+          const double fp = (double)P.pre, fm = (double)P.max_samples;
+          ax = (ax * fp + 0.0) / fm; ay = (ay * fp + 0.0) / fm; az = (az * fp + 0.0) / fm;
+        }
+      }
+    }
+    if (resolver && !queued) write_pixel(P, x, y, ax, ay, az);
+  } else if (active) {
+    double* out = P.samples + w * 3ull;
+    out[0] = col.x; out[1] = col.y; out[2] = col.z;
+  }
+  flush_ctx(P, ctx, x, y, active);
+}
 
 }  // namespace rtrb

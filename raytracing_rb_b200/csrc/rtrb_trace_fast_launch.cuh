@@ -1,0 +1,94 @@
+// rtrb_trace_fast_launch.cuh — kernels and launchers of the FAST64 trace path, instantiated per stack capacity
+// in separate translation units (rtrb_trace_fast_d1.cu, _t10.cu, _t32.cu, _t128.cu) so they compile in parallel.
+#pragma once
+#include "rtrb_launch.h"
+#include "rtrb_trace_fast.cuh"
+
+namespace rtrb_fast {
+
+// Launch shape per kernel family (16 warps per SM at 128 registers either way; measured on B200, profiles/README.md):
+//   depth-1 kernels (MAXS == 1): 128 threads x 4 CTAs per SM  (256 x 2 is 5 % slower on config 2)
+//   ray-tree kernels (MAXS > 1): lockstep item loop, so the CTA is the unit that shares the instruction caches:
+//                                512 threads x 1 CTA per SM on frames of more than a few waves (config 4: 4.44 / 3.78 /
+//                                3.57 ms and config 5: 5.13 / 4.61 / 4.24 ms with 128 / 256 / 512 threads; config 3:
+//                                3.87 / 3.44 / 3.52), 128 threads on small frames
+constexpr int kFastBlock = 128, kFastMinBlocks = 4, kTreeBlock = 512, kTreeMinBlocks = 1;
+
+template <int MAXS, bool DETAIL, bool BVH>
+__global__ void __launch_bounds__(kFastBlock, kFastMinBlocks) trace_pre_fast_kernel(const __grid_constant__ FrameParams P) {
+  rtrb::trace_pre_body<MAXS, DETAIL, BVH ? 2 : 1>(P);
+}
+template <int MAXS, bool DETAIL, bool BVH>
+__global__ void __launch_bounds__(kTreeBlock, kTreeMinBlocks) trace_pre_tree_kernel(const __grid_constant__ FrameParams P) {
+  rtrb::trace_pre_tree_body<MAXS, BVH, DETAIL>(P);
+}
+template <int MAXS, bool DETAIL, bool BVH>
+__global__ void __launch_bounds__(kFastBlock, kFastMinBlocks) trace_extra_fast_kernel(const __grid_constant__ FrameParams P) {
+  rtrb::trace_extra_body<MAXS, DETAIL, BVH ? 2 : 1>(P);
+}
+
+inline int sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+// depth-1 frames: one thread per (pixel, sample)
+template <bool DETAIL>
+cudaError_t launch_pre_d1(const FrameParams& P, cudaStream_t s) {
+  const unsigned long long total = (unsigned long long)P.n_tiles * RTRB_SUPER_PIXELS * (unsigned long long)P.pre;
+  if (total == 0) return cudaSuccess;
+  const unsigned long long blocks = (total + kFastBlock - 1) / kFastBlock;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  if (P.use_bvh) trace_pre_fast_kernel<1, DETAIL, true><<<(unsigned)blocks, kFastBlock, 0, s>>>(P);
+  else trace_pre_fast_kernel<1, DETAIL, false><<<(unsigned)blocks, kFastBlock, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+// ray-tree frames: one thread per (pixel, sample), lockstep CTAs (rtrb_trace_fast.cuh, trace_pre_tree_body)
+template <int MAXS, bool DETAIL>
+cudaError_t launch_pre_tree(const FrameParams& P, cudaStream_t s) {
+  const unsigned long long total = (unsigned long long)P.n_tiles * RTRB_SUPER_PIXELS * (unsigned long long)P.pre;
+  if (total == 0) return cudaSuccess;
+  int block = kTreeBlock;
+  if (total < 4ull * (unsigned long long)sm_count() * kTreeBlock) block = 128;  // small frames: more, smaller CTAs
+  const unsigned long long blocks = (total + block - 1) / block;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  // in-CTA resolve (fuse_resolve == 2): the host only selects it for sample counts that divide both CTA sizes
+  if (P.fuse_resolve == 2 && (block % P.pre) != 0) return cudaErrorInvalidConfiguration;
+  const size_t smem = P.fuse_resolve == 2 ? (size_t)block * 3u * sizeof(double) : 0u;
+  if (P.use_bvh) trace_pre_tree_kernel<MAXS, DETAIL, true><<<(unsigned)blocks, block, smem, s>>>(P);
+  else trace_pre_tree_kernel<MAXS, DETAIL, false><<<(unsigned)blocks, block, smem, s>>>(P);
+  return cudaGetLastError();
+}
+
+template <int MAXS, bool DETAIL>
+cudaError_t launch_extra(const FrameParams& P, cudaStream_t s) {
+  const int sms = sm_count();
+  if (P.use_bvh) trace_extra_fast_kernel<MAXS, DETAIL, true><<<sms * 8, kFastBlock, 0, s>>>(P);
+  else trace_extra_fast_kernel<MAXS, DETAIL, false><<<sms * 8, kFastBlock, 0, s>>>(P);
+  return cudaGetLastError();
+}
+
+// per-capacity entry points, one translation unit each
+cudaError_t pre_d1(const FrameParams& P, cudaStream_t s);
+cudaError_t extra_d1(const FrameParams& P, cudaStream_t s);
+cudaError_t pre_t10(const FrameParams& P, cudaStream_t s);
+cudaError_t extra_t10(const FrameParams& P, cudaStream_t s);
+cudaError_t pre_t32(const FrameParams& P, cudaStream_t s);
+cudaError_t extra_t32(const FrameParams& P, cudaStream_t s);
+cudaError_t pre_t128(const FrameParams& P, cudaStream_t s);
+cudaError_t extra_t128(const FrameParams& P, cudaStream_t s);
+
+}  // namespace rtrb_fast
+
+#define RTRB_FAST_TREE_TU(N)                                                                         \
+  namespace rtrb_fast {                                                                              \
+  cudaError_t pre_t##N(const FrameParams& P, cudaStream_t s) {                                       \
+    return P.count_detail ? launch_pre_tree<N, true>(P, s) : launch_pre_tree<N, false>(P, s);        \
+  }                                                                                                  \
+  cudaError_t extra_t##N(const FrameParams& P, cudaStream_t s) {                                     \
+    return P.count_detail ? launch_extra<N, true>(P, s) : launch_extra<N, false>(P, s);              \
+  }                                                                                                  \
+  }

@@ -18,6 +18,8 @@
 #define RTRB_APEX_MAX 32              // linear-filter scenes (<= 32 spheres) get apex tables, see FrameParams
 #define RTRB_K_PLANES 8               // ... have at most this many planes
 #define RTRB_K_LIGHTS 2               // ... and at most this many lights (anything larger runs the BVH kernels)
+#define RTRB_TREE_MIN_BLOCK 128        // smallest CTA the ray-tree kernels are launched with (the largest is 512): a
+                                      // pre_sample_times that divides it has every sample of a pixel in one CTA
 
 struct DevGeom {      // 64 B
   double px, py, pz;  // sphere centre / plane point
@@ -132,9 +134,13 @@ struct FrameParams {
   uint32_t* extra_count;       // number of pixels taking the extra-sample branch
   uint32_t* extra_list;        // [n_tiles*1024] pixel slots (tile k * 1024 + q)
   double* extra_samples;       // [extra][max-pre][3]
-  unsigned long long* work_counter;  // [2] persistent-kernel work claim counters (pre pass, extra pass)
+  double* pre_avg;             // [extra][3] mean of the pre samples of the queued pixels (fuse_resolve == 2 only)
+  unsigned long long* work_counter;  // [2] spare work-claim counters (zeroed with the control block)
   int32_t count_detail;
-  int32_t fuse_resolve;        // pre == max == 1 style frames: the trace kernel writes the pixel itself
+  int32_t fuse_resolve;        // who finishes render_at: 0 = resolve_kernel from the sample buffer; 1 = the trace
+                               // kernel, one sample per pixel (mean = the sample, variance 0); 2 = the ray-tree
+                               // kernels, in the CTA that traced the pixel's samples (ordered mean + variance test
+                               // from shared memory)
   int32_t pixel_format;        // RTRB_FMT_*: 4 (RGBA8) or 3 (RGB8) bytes per pixel in `rgba`
   // whole frame on one renderer: tile k is (k % stx_count, k / stx_count), no table load at kernel start;
   // k / stx_count == __umulhi(k, tiles_magic), verified on the host for every k < n_tiles

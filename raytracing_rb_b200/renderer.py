@@ -94,7 +94,7 @@ class Renderer:
 
     def submit(self, cam, out_rgba, opts=None):
         """Pipelined frame: returns a ticket at once; the RGBA8 frame lands in `out_rgba` (a numpy view
-        of pinned host memory for full speed) by the time `wait(ticket)` returns.  Two in flight."""
+        of pinned host memory for full speed) by the time `wait(ticket)` returns.  Up to four in flight."""
         opts = opts or make_opts()
         t = C.c_int()
         check(lib().rtrb_submit(self._h, C.byref(cam), C.byref(opts), out_rgba.ctypes.data, C.byref(t)))
@@ -126,6 +126,10 @@ class Renderer:
     def framebuffer_download(self, width, height, out):
         check(lib().rtrb_framebuffer_download(self._h, width, height, out.ctypes.data))
         return out
+
+    def framebuffer_copy_async(self, nbytes, out, stream=None):
+        """Queues framebuffer[:nbytes] -> `out` (pinned host memory) on `stream`; the caller synchronises."""
+        check(lib().rtrb_framebuffer_copy_async(self._h, nbytes, out.ctypes.data, C.c_void_p(stream) if stream else None))
 
     def framebuffer_ipc_export(self, width, height):
         buf = (C.c_uint8 * 64)()
