@@ -134,7 +134,19 @@ __device__ __forceinline__ bool sphere_intersect(const DevGeom& g, d3 o, d3 d, d
   if (!(nd <= g.radius)) return false;  // unless inner?(nearest_point)
   double hh = sqrt(g.radius * g.radius - nd * nd);
   d3 vec = dn * hh;
-  bool from_inner = norm(oc) <= g.radius;  // |O - C| == |C - O| bit for bit
+  // from_inner = |O - C| <= R (|O - C| == |C - O| bit for bit)
+#ifdef RTRB_FAST_TU
+  // FAST64 translation units: sqrt is monotone and correctly rounded, so away from the surface the comparison of the
+  // squares decides (1e-14 >> 2^-52 covers the roundings of R*R and of the sum); inside that band, and for NaNs,
+  // negative or overflowing radii, the reference's own expression is evaluated.
+  const double oc2 = sumsq(oc), rr2 = g.radius * g.radius;
+  bool from_inner;
+  if (g.radius >= 0 && rr2 < 1e300 && oc2 < rr2 * (1.0 - 1e-14)) from_inner = true;
+  else if (g.radius >= 0 && rr2 < 1e300 && oc2 > rr2 * (1.0 + 1e-14)) from_inner = false;
+  else from_inner = sqrt(oc2) <= g.radius;
+#else
+  const bool from_inner = norm(oc) <= g.radius;
+#endif
   h.dir_in = !from_inner;
   h.p = h.dir_in ? (np - vec) : (np + vec);
   if (!from_inner && t < 0) return false;
@@ -285,14 +297,24 @@ __device__ __forceinline__ d3 a_vertical_vector(d3 n, ThreadCtx& ctx) {
   return mk(-(n.y + n.z) / n.x, 1.0, 1.0);
 }
 
+// Float#to_i then Integer#% (texture.rb:24-25): truncation toward zero, then FLOORED modulo by a positive size.
+// `t` is already truncated.  Values that fit 32 bits take the integer path (the remainder of an integer division is
+// exact either way, so the result equals fmod's: -2.6 % instructions on config 3); anything larger goes through fmod.
+__device__ __forceinline__ int trunc_mod(double t, int n) {
+  if (fabs(t) < 2147483648.0) {
+    int m = (int)t % n;
+    return m < 0 ? m + n : m;
+  }
+  double m = m_fmod(t, (double)n);
+  if (m < 0) m += n;
+  return (int)m;
+}
+
 // Texture#color (texture.rb:23-28)
 __device__ __forceinline__ d3 texture_color(const DevMat& m, double uu, double vv, ThreadCtx& ctx) {
   double fu = (uu + m.uoff) / m.hscale, fv = (vv + m.voff) / m.vscale;
   if (!isfinite(fu) || !isfinite(fv)) { ctx.status |= RTRB_ST_NAN_TO_INT; return mk(0, 0, 0); }
-  double mu = m_fmod(trunc(fu), (double)m.tex_w), mv = m_fmod(trunc(fv), (double)m.tex_h);
-  if (mu < 0) mu += m.tex_w;
-  if (mv < 0) mv += m.tex_h;
-  int u = (int)mu, v = (int)mv;
+  const int u = trunc_mod(trunc(fu), m.tex_w), v = trunc_mod(trunc(fv), m.tex_h);
   const uint8_t* p = m.tex + ((size_t)v * m.tex_w + u) * 3;
   return mk(__ldg(p) / 256.0, __ldg(p + 1) / 256.0, __ldg(p + 2) / 256.0);
 }

@@ -16,6 +16,7 @@
 // Compiled with -fmad=false as well: the exact parts must not contract; the FP32 filter uses
 // explicit fmaf().
 #pragma once
+#define RTRB_FAST_TU 1  // exact-preserving shortcuts inside the shared STRICT functions (rtrb_trace.cuh)
 #include "rtrb_trace.cuh"
 
 namespace rtrb {
@@ -995,7 +996,34 @@ __device__ __forceinline__ void trace_pre_tree_body(const FrameParams& P) {
     __syncthreads();
     const bool resolver = active && j == 0u;
     double ax = 0, ay = 0, az = 0, variance = 0;
-    if (resolver) pre_mean_of(mine, (int)S, ax, ay, az, variance);
+    if (S < 8u) {
+      if (resolver) pre_mean_of(mine, (int)S, ax, ay, az, variance);
+    } else {
+      // Many samples per pixel: the ORDER of both sums is the reference's (sample 0 first, camera.rb:79-86), but the
+      // three channels of the mean run on three threads and every thread forms its own squared deviation, so the
+      // CTA's tail is two serial chains of S additions instead of one of 9 S operations.
+      double* first = mine - (size_t)j * 3u;            // sample 0 of this thread's pixel
+      double m = 0.0;
+      if (active && j < 3u) {
+        for (uint32_t k = 0; k < S; ++k) m += first[k * 3u + j];
+        m = m / (double)S;
+      }
+      __syncthreads();                                  // every thread has read what the next store overwrites
+      const double cx = mine[0], cy = mine[1], cz = mine[2];
+      __syncthreads();
+      if (active && j < 3u) first[j] = m;               // the pixel's mean replaces sample 0's colour
+      __syncthreads();
+      ax = first[0]; ay = first[1]; az = first[2];
+      const double dx = cx - ax, dy = cy - ay, dz = cz - az;
+      const double mm = fmax(dx, fmax(dy, dz));         // (sample - mean).to_a.max, signed
+      __syncthreads();
+      mine[0] = mm * mm;
+      __syncthreads();
+      if (resolver) {
+        for (uint32_t k = 0; k < S; ++k) variance += first[k * 3u];
+        variance /= (double)S;
+      }
+    }
     const bool adaptive = resolver && variance >= P.variant_threshold;
     // pixels that take the extra-sample branch (camera.rb:87-93): one ballot per warp, list positions by prefix
     // popcount, one atomic per warp and counter
