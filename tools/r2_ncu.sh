@@ -14,7 +14,7 @@ for c in "$@"; do
     5s) ARGS="5 --width 480 --height 270 --spp 4 --frames 2";;
   esac
   python tools/run_config.py $ARGS > $O/plain_c$c.log 2>&1 &&
-  $NCU -k regex:trace_pre_fast -s 1 -c 1 -o $O/c$c -f python tools/run_config.py $ARGS > $O/ncu_c$c.log 2>&1
+  $NCU -k regex:trace_pre_ -s 1 -c 1 -o $O/c$c -f python tools/run_config.py $ARGS > $O/ncu_c$c.log 2>&1
   python tools/ncu_summary.py $O/c$c.ncu-rep "config $c ($ARGS) $TAG" > $O/summary_c$c.txt 2>&1
   ncu -i $O/c$c.ncu-rep --page source --csv 2>/dev/null | gzip > $O/source_c$c.csv.gz
   ncu -i $O/c$c.ncu-rep --page raw --csv 2>/dev/null | gzip > $O/raw_c$c.csv.gz
