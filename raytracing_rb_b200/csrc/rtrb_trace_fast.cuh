@@ -279,7 +279,9 @@ __device__ __forceinline__ bool bvh_traverse(const FrameParams& P, const BvhRay&
 template <bool BOX>
 __device__ __forceinline__ int closest_hit_bvh(const FrameParams& P, d3 o, d3 d, const CullRay& r, HitRec& bh,
                                                 ThreadCtx& ctx) {
-  if (P.n_sph > 0xFFFFF || P.n_pl > 8) return closest_hit_scan_call<BOX>(P, o, d, bh, ctx);
+  // Pack8 keeps survivor slots in 16 bits: the BVH filter serves scenes of up to 65 536 bounded objects (larger ones
+  // take the reference's own scan: correct, but brute force)
+  if (P.n_sph > 0x10000 || P.n_pl > 8) return closest_hit_scan_call<BOX>(P, o, d, bh, ctx);
   // pass 1a: planes bound the search first (nothing at or beyond max_distance can win, world.rb:39)
   float best_hi = P.max_distance_f;
   for (int k = 0; k < P.n_pl; ++k) {
@@ -360,7 +362,7 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
     const float lx = (float)c.lt.x, ly = (float)c.lt.y, lz = (float)c.lt.z;
     far = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) * 1.00001f + 2.0f * r.E;
   }
-  if (P.n_sph > 0xFFFFF || P.n_pl > 0xFFFF) return lit_area_call<BOX>(P, target, L, ctx);
+  if (P.n_sph > 0x10000 || P.n_pl > 0xFFFF) return lit_area_call<BOX>(P, target, L, ctx);
   Pack8 S, Q;
   S.clear();
   Q.clear();

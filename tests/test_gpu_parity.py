@@ -388,3 +388,25 @@ def test_stochastic_configs_psnr_vs_high_spp_reference(oracle_mod, config_id, kw
     p = psnr_u8(got.rgba, ref.rgba)
     print("config %d: PSNR %.2f dB (GPU at configured spp vs oracle at %d spp)" % (config_id, p, spp_hi))
     assert p >= 40.0
+
+
+def test_more_spheres_than_the_filter_can_index(oracle_mod):
+    """The BVH filter packs survivor indices into 16 bits; a scene with more than 65 536 spheres must fall back to
+    the reference's own scan instead of truncating indices (latent in round 1: the guard sat at 2^20).  Small
+    spheres on a fine grid, so that most primary rays have a survivor with a high index."""
+    from raytracing_rb_b200 import Camera, World, scenes
+    rs = np.random.RandomState(3)
+    n = 66000
+    objs = [scenes.ground()]
+    gy, gx = np.meshgrid(np.linspace(-8, 8, 250), np.linspace(30, 3, 264))  # far rows first: the near spheres get the high indices
+    for k, (x, y) in enumerate(zip(gx.ravel()[:n], gy.ravel()[:n])):
+        r = 0.02 + 0.01 * rs.uniform()
+        objs.append(scenes.matte("m%d" % k, (float(x), float(y), -1 + r), r, (0.9, 0.5, 0.4)))
+    w = World({"max_distance": 10000, "soft_shadow_exponent": 2, "lights": [scenes.light([5, -4, 4], 0.0)],
+               "world_objects": objs})
+    _, cdoc = scenes.build(2, width=48, height=27)
+    cam = Camera(w, dict(cdoc, trace_depth=2))
+    ref = oracle_mod.OracleScene(w.to_scene_desc()).render(cam.camera_desc(), make_opts(seed=1))
+    got = cam.render_frame(seed=1, precision=PREC_FAST64, count_detail=True)
+    assert (got.hit > 65536).sum() > 0, "the test needs primary hits on high-index spheres"
+    check(ref, got, False)
