@@ -35,3 +35,6 @@ for i in range(a.frames):
     print("config %d %dx%d spp %d frame %d: device %.3f ms  trace %.3f ms  %.2f M ray queries  %.1f Mrays/s" % (
         a.config, cd.width, cd.height, cd.pre_sample_times, i, st["device_ms"], st["trace_ms"], q / 1e6,
         q / st["device_ms"] / 1e3), flush=True)
+    if a.detail:
+        print("   detail: rays %d hits %d exact %d box_tests %d box_accepts %d cover_box %d" % (
+            st["rays"], st["hits"], st["exact_tests"], st["box_tests"], st["box_accepts"], st["cover_box"]), flush=True)
