@@ -7,12 +7,17 @@
 namespace rtrb_fast {
 
 // Launch shape per kernel family (16 warps per SM at 128 registers either way; measured on B200, profiles/README.md):
-//   depth-1 kernels (MAXS == 1): 128 threads x 4 CTAs per SM  (256 x 2 is 5 % slower on config 2)
+//   depth-1 kernels (MAXS == 1): 128 threads x 5 CTAs per SM = 96 registers (round 2, config 2: 0.101 ms at 4 CTAs /
+//                                128 registers, 0.095 - 0.098 at 5 .. 8 CTAs / 96 .. 64 registers; 256 x 2: 0.103).
+//                                The extra-sample kernels keep 4 CTAs (config 1: 0.707 vs 0.735 ms)
 //   ray-tree kernels (MAXS > 1): lockstep item loop, so the CTA is the unit that shares the instruction caches:
 //                                512 threads x 1 CTA per SM on frames of more than a few waves (config 4: 4.44 / 3.78 /
 //                                3.57 ms and config 5: 5.13 / 4.61 / 4.24 ms with 128 / 256 / 512 threads; config 3:
 //                                3.87 / 3.44 / 3.52), 128 threads on small frames
-constexpr int kFastBlock = 128, kFastMinBlocks = 4, kTreeBlock = 512, kTreeMinBlocks = 1;
+#ifndef RTRB_FAST_MIN_BLOCKS
+#define RTRB_FAST_MIN_BLOCKS 5
+#endif
+constexpr int kFastBlock = 128, kFastMinBlocks = RTRB_FAST_MIN_BLOCKS, kExtraMinBlocks = 4, kTreeBlock = 512, kTreeMinBlocks = 1;
 
 template <int MAXS, bool DETAIL, bool BVH>
 __global__ void __launch_bounds__(kFastBlock, kFastMinBlocks) trace_pre_fast_kernel(const __grid_constant__ FrameParams P) {
@@ -23,7 +28,7 @@ __global__ void __launch_bounds__(kTreeBlock, kTreeMinBlocks) trace_pre_tree_ker
   rtrb::trace_pre_tree_body<MAXS, BVH, DETAIL>(P);
 }
 template <int MAXS, bool DETAIL, bool BVH>
-__global__ void __launch_bounds__(kFastBlock, kFastMinBlocks) trace_extra_fast_kernel(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kFastBlock, kExtraMinBlocks) trace_extra_fast_kernel(const __grid_constant__ FrameParams P) {
   rtrb::trace_extra_body<MAXS, DETAIL, BVH ? 2 : 1>(P);
 }
 
