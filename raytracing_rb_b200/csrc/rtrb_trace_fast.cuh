@@ -630,6 +630,18 @@ __device__ __forceinline__ double lit_area_fast(const FrameParams& P, d3 target,
   else return lit_area_linear<BOX, KT>(P, target, L, light_index, ctx);
 }
 
+// The reference's own expression of the highlight match (world.rb:86-93), register-only interface.
+static __device__ __noinline__ bool highlight_match_exact(double lx, double ly, double lz, double threshold, double ox, double oy,
+                                                         double oz, double dx, double dy, double dz, uint32_t* status) {
+  ThreadCtx t;
+  t.status = 0; t.detail = false;
+  const d3 a = mk(lx, ly, lz) - mk(ox, oy, oz);
+  const double ct = vcos(mk(dx, dy, dz), a, t);
+  const double ang = rb_acos(ct, t);
+  *status = t.status;
+  return ang < threshold;
+}
+
 // World#high_lights match for one light (world.rb:86-93): acos(|cos|) < threshold, filtered in FP32 on
 // cos^2 against cos^2(threshold); the exact FP64 expression decides only inside the error band.
 __device__ __forceinline__ bool highlight_match_fast(const DevLight& L, const DevLightF& F, d3 o, d3 d,
@@ -647,10 +659,19 @@ __device__ __forceinline__ bool highlight_match_fast(const DevLight& L, const De
     if (c2 + tol < F.cos2_thr) return false;
   }
   // exact (also reached for thresholds outside (0, 90 degrees), NaNs, and rays starting at the light)
+#ifdef RTRB_OUTLINE_LIBM
+  // depth-1 translation unit: rare there, and out of line so that its two divisions, square root and acos do not sit
+  // between the hot blocks (config 2: -1 %; the ray-tree kernels lose 1 % with it and keep the inline form)
+  uint32_t st = 0u;
+  const bool hit = highlight_match_exact(L.px, L.py, L.pz, L.hl_threshold, o.x, o.y, o.z, d.x, d.y, d.z, &st);
+  ctx.status |= st;
+  return hit;
+#else
   d3 a = mk(L.px, L.py, L.pz) - o;
   double ct = vcos(d, a, ctx);
   double ang = rb_acos(ct, ctx);
   return ang < L.hl_threshold;
+#endif
 }
 
 // `attenuation.r < 0.0001` (ray_tracer.rb:52) without the square root outside a narrow band.
@@ -705,6 +726,27 @@ __device__ __forceinline__ int item_phase_a(const FrameParams& P, const StackIte
   if (is_first) *primary_hit = best_i;
   RTRB_COUNT(ctx, RTRB_CNT_HITS);
   return best_i;
+}
+
+// trace_depth <= 1, near normal incidence: the direction math of the children that are born dead (world_object.rb:121-137)
+// is evaluated only for the conditions it could raise on.  Rare; out of line with a register-only interface.
+static __device__ __noinline__ uint32_t born_dead_children_status(double dx, double dy, double dz, double nx, double ny, double nz,
+                                                                 double nnx, double nny, double nnz, double rate, bool can_refract) {
+  ThreadCtx t;
+  t.status = 0; t.detail = false;
+  const d3 d = mk(dx, dy, dz), n = mk(nx, ny, nz), nn = mk(nnx, nny, nnz);
+  const double d_r = norm(d);
+  const double cos_theta = vcos(d, -n, t);
+  const d3 refl_dir = normalize(nn * (2 * cos_theta * d_r) + d, t);
+  if (can_refract) {
+    const double sin_i = rb_sqrt(1 - cos_theta * cos_theta, t);
+    const double sin_r = sin_i / rate;
+    if (!(sin_r >= 1)) {
+      if (sin_r < -1 || sin_r > 1) t.status |= RTRB_ST_MATH_DOMAIN;
+      (void)normalize(refl_dir + d, t);
+    }
+  }
+  return t.status;
 }
 
 template <int MAXS, bool BVH, bool BOX>
@@ -764,19 +806,7 @@ __device__ __forceinline__ void item_phase_b(const FrameParams& P, const StackIt
     if constexpr (MAXS == 1) {
       // trace_depth <= 1: every child is born with depth 0 and dropped at ray_tracer.rb:52; only the
       // raise sites of their direction math can be observed, and only near normal incidence
-      if (near_normal) {
-        const double d_r = norm(d);
-        const double cos_theta = vcos(d, -n, ctx);
-        const d3 refl_dir = normalize(nn * (2 * cos_theta * d_r) + d, ctx);
-        if (can_refract) {
-          const double sin_i = rb_sqrt(1 - cos_theta * cos_theta, ctx);
-          const double sin_r = sin_i / rate;
-          if (!(sin_r >= 1)) {
-            if (sin_r < -1 || sin_r > 1) ctx.status |= RTRB_ST_MATH_DOMAIN;
-            (void)normalize(refl_dir + d, ctx);
-          }
-        }
-      }
+      if (near_normal) ctx.status |= born_dead_children_status(d.x, d.y, d.z, n.x, n.y, n.z, nn.x, nn.y, nn.z, rate, can_refract);
     } else if (refl_alive || refr_alive || near_normal) {
       if (sp + 2 > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; return; }
       const double d_r = norm(d);
