@@ -241,7 +241,14 @@ __device__ __forceinline__ double cover_object_exact(const FrameParams& P, const
     double dd = norm(x1 - cc);
     if (dd >= r1 + g.radius) return 0;
     double s1 = RTRB_PI * r1 * r1;
+#ifdef RTRB_LEAN_SCENE
+    // light_radius == 0.0, so r1 is a zero or a NaN (0 * inf).  Past the test above dd < R (or a comparison with a NaN
+    // failed); then `dd > |R - r1|` = `dd > |R|` cannot hold (R >= 0: dd < R; R < 0: no dd >= 0 is < R; NaN: false), so
+    // the partial-overlap branch (sphere.rb:37-47) is unreachable and its acos / sin / divisions are not compiled in
+    if (false) {
+#else
     if (dd > fabs(g.radius - r1)) {
+#endif
       RTRB_COUNT(ctx, RTRB_CNT_COV_SPH_PEN);
       double ct1 = fmin((r1 * r1 + dd * dd - g.radius * g.radius) / (2 * r1 * dd), 1.0);
       double ct2 = fmin((g.radius * g.radius + dd * dd - r1 * r1) / (2 * g.radius * dd), 1.0);

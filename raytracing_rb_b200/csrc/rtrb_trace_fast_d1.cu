@@ -7,11 +7,11 @@
 #define RTRB_OUTLINE_LIBM 1
 #endif
 #include "rtrb_trace_fast_launch.cuh"
-namespace rtrb_fast {
+namespace RTRB_FAST_NS {
 cudaError_t pre_d1(const FrameParams& P, cudaStream_t s) {
   return P.count_detail ? launch_pre_d1<true>(P, s) : launch_pre_d1<false>(P, s);
 }
 cudaError_t extra_d1(const FrameParams& P, cudaStream_t s) {
   return P.count_detail ? launch_extra<1, true>(P, s) : launch_extra<1, false>(P, s);
 }
-}  // namespace rtrb_fast
+}  // namespace RTRB_FAST_NS

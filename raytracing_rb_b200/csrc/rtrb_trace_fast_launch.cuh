@@ -4,7 +4,10 @@
 #include "rtrb_launch.h"
 #include "rtrb_trace_fast.cuh"
 
-namespace rtrb_fast {
+#ifndef RTRB_FAST_NS
+#define RTRB_FAST_NS rtrb_fast  // the lean-scene build of the depth-1 kernels lives in rtrb_fast_lean
+#endif
+namespace RTRB_FAST_NS {
 
 // Launch shape per kernel family (16 warps per SM at 128 registers either way; measured on B200, profiles/README.md):
 //   depth-1 kernels (MAXS == 1): 128 threads x 5 CTAs per SM = 96 registers (round 2, config 2: 0.101 ms at 4 CTAs /
@@ -86,10 +89,10 @@ cudaError_t extra_t32(const FrameParams& P, cudaStream_t s);
 cudaError_t pre_t128(const FrameParams& P, cudaStream_t s);
 cudaError_t extra_t128(const FrameParams& P, cudaStream_t s);
 
-}  // namespace rtrb_fast
+}  // namespace RTRB_FAST_NS
 
 #define RTRB_FAST_TREE_TU(N)                                                                         \
-  namespace rtrb_fast {                                                                              \
+  namespace RTRB_FAST_NS {                                                                              \
   cudaError_t pre_t##N(const FrameParams& P, cudaStream_t s) {                                       \
     return P.count_detail ? launch_pre_tree<N, true>(P, s) : launch_pre_tree<N, false>(P, s);        \
   }                                                                                                  \

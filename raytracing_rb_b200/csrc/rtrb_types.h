@@ -103,7 +103,10 @@ struct FrameParams {
   const DevLightF* lights_f;   // [n_lights]
   const struct BvhNode* bvh;   // sphere BVH over cull_sph[] (rtrb_bvh.h); node 0 = root
   int32_t n_sph, n_pl;
-  int32_t use_bvh, pad_bvh;    // > RTRB_BVH_MIN_SPHERES spheres: BVH kernels; else the linear-scan kernels
+  int32_t use_bvh;             // > RTRB_BVH_MIN_SPHERES spheres: BVH kernels; else the linear-scan kernels
+  int32_t lean_scene;          // 1: ONE light of radius exactly 0 (hard shadows), no textured object, soft_shadow_exponent
+                               // == 2: depth-1 frames run kernels compiled without the code such a scene cannot reach
+                               // (rtrb_trace_fast_d1lean.cu); results are the generic kernels' bit for bit
   // Apex tables (linear-filter scenes only): rays that pass through a known point A — primary rays
   // through the lens centre (within aperture_radius), shadow probes through their light — test sphere k
   // with b = v.u, survive unless b*b < Kq, where (v, Kq) = (C - A, |v|^2 - (R + margins)^2 - slack)

@@ -410,3 +410,49 @@ def test_more_spheres_than_the_filter_can_index(oracle_mod):
     got = cam.render_frame(seed=1, precision=PREC_FAST64, count_detail=True)
     assert (got.hit > 65536).sum() > 0, "the test needs primary hits on high-index spheres"
     check(ref, got, False)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_lean_scene_kernels_match_the_generic_path(oracle_mod, seed):
+    """Scenes with ONE light of radius exactly 0, no textures and soft_shadow_exponent 2 run depth-1 frames on kernels
+    compiled without the code such a scene cannot reach (rtrb_trace_fast_d1lean.cu: light loops, pow, texture lookup,
+    the penumbra branch of Sphere#cover_area).  They must reproduce STRICT bit for bit and the oracle's frame, also
+    with the camera inside a sphere, spheres cut by planes, a glassy plane, 1 and 3 samples per pixel and the adaptive
+    pass; a light radius of 1e-300 or a second light must fall back to the generic kernels with the same result."""
+    from raytracing_rb_b200 import Camera, World, scenes
+    rs = np.random.RandomState(100 + seed)
+    objs = [scenes.ground()]
+    if seed % 3 == 1:
+        w2 = scenes.wall(14)
+        for k in ("texture_file_path", "texture_horizontal_scale", "texture_vertical_scale"):
+            w2["properties"].pop(k)
+        w2["properties"].update(refractive_rate=1.3, refractive_attenuation=[0.2, 0.2, 0.2], diffuse_rate=[0.4, 0.4, 0.4])
+        objs.append(w2)
+    for k in range(int(rs.randint(0, 20))):
+        r = float(rs.uniform(0.1, 1.2))
+        c = (float(rs.uniform(1.5, 12)), float(rs.uniform(-5, 5)), float(rs.uniform(-1.2, 1.0)))
+        objs.append(scenes.glass("g%d" % k, c, r) if k % 3 == 0 else scenes.matte("m%d" % k, c, r, rs.uniform(0.3, 1, 3)))
+    if seed == 5:
+        objs.append(scenes.glass("around the camera", (0.2, 0.1, 0.0), 1.5))
+    lpos = [float(rs.uniform(2, 9)), float(rs.uniform(-5, 5)), float(rs.uniform(0.5, 6))]
+    variants = [("lean", [scenes.light(lpos, 0.0)])]
+    if seed == 0:
+        variants += [("tiny radius", [scenes.light(lpos, 1e-300)]), ("two lights", [scenes.light(lpos, 0.0), scenes.light([3, 2, 5], 0.0)])]
+    _, cdoc = scenes.build(2, width=96, height=54)
+    if seed % 2 == 1:
+        cdoc = dict(cdoc, pre_sample_times=3, max_sample_times=7, variant_threshold=1e-5, aperture_radius=0.002)
+    for label, lights in variants:
+        world = World({"max_distance": 10000, "soft_shadow_exponent": 2, "lights": lights, "world_objects": objs})
+        cam = Camera(world, cdoc)
+        ref = oracle_mod.OracleScene(world.to_scene_desc()).render(cam.camera_desc(), make_opts(seed=seed))
+        a = cam.render_frame(seed=seed, precision=PREC_STRICT, count_detail=True)
+        b = cam.render_frame(seed=seed, precision=PREC_FAST64, count_detail=True)
+        c = cam.render_frame(seed=seed, precision=PREC_FAST64, count_detail=False)
+        assert np.array_equal(a.rgb, b.rgb) and np.array_equal(a.rgba, b.rgba) and np.array_equal(a.hit, b.hit), label
+        assert np.array_equal(b.rgba, c.rgba) and np.array_equal(b.hit, c.hit), label
+        assert ref.stats["status"] == b.stats["status"], label
+        frac, maxdiff, ndiff = compare_u8(b.rgba, ref.rgba)
+        assert ndiff == 0 and np.array_equal(b.hit, ref.hit), (label, ndiff, maxdiff)
+        for k in ("samples", "rays", "shadow_queries", "hits", "local_shaded", "lit_lights", "adaptive_pixels", "status"):
+            assert a.stats[k] == b.stats[k] == ref.stats[k], (label, k)
+        assert c.stats["rays"] == b.stats["rays"] and c.stats["shadow_queries"] == b.stats["shadow_queries"]
