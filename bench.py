@@ -148,19 +148,27 @@ def config_record(name, cdoc):
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
-def is_lean_scene(world):
-    """rtrb_api.cu's scene class `lean_scene`: one light of radius exactly 0, no textured object, exponent 2."""
-    return (len(world.lights) == 1 and float(world.lights[0].radius) == 0.0 and float(world.soft_shadow_exponent) == 2.0
-            and not any(o.texture is not None and type(o).__name__ != "Box" for o in world.world_objects))
+def scene_class(world):
+    """rtrb_api.cu's scene classes (FrameParams::scene_class): "one_light" = exactly one light and soft_shadow_exponent
+    == 2; "lean" = that, the light's radius exactly 0 and no textured object; else "generic"."""
+    if not (len(world.lights) == 1 and float(world.soft_shadow_exponent) == 2.0):
+        return "generic"
+    textured = any(o.texture is not None and type(o).__name__ != "Box" for o in world.world_objects)
+    return "lean" if float(world.lights[0].radius) == 0.0 and not textured else "one_light"
 
 
-def kernel_name(cd, n_spheres, lean=False):
-    """The template instantiation rtrb_launch_trace_pre_fast dispatches this frame to (rtrb_trace_fast.cu)."""
+def kernel_name(cd, n_spheres, klass="generic"):
+    """The kernel build and template instantiation rtrb_launch_trace_pre_fast dispatches this frame to
+    (rtrb_trace_fast.cu): namespace = scene / frame class, template arguments = <stack capacity, DETAIL, BVH>."""
     bvh = "true" if n_spheres > 32 else "false"
     if cd.trace_depth <= 1:
-        return "%s::trace_pre_fast_kernel<1,false,%s>" % ("rtrb_fast_lean" if lean else "rtrb_fast", bvh)
+        return "%s::trace_pre_fast_kernel<1,false,%s>" % ("rtrb_fast_lean" if klass == "lean" else "rtrb_fast", bvh)
     need = cd.trace_depth * (1 + cd.monte_carlo_diffusion_times) + 1
-    return "rtrb_fast::trace_pre_tree_kernel<%d,false,%s>" % (10 if need <= 10 else 32 if need <= 32 else 128, bvh)
+    cap = 10 if need <= 10 else 32 if need <= 32 else 128
+    ns = "rtrb_fast"
+    if klass in ("one_light", "lean") and cap <= 32:
+        ns = "rtrb_fast_l1n" if cd.monte_carlo_diffusion_times == 0 else "rtrb_fast_l1"
+    return "%s::trace_pre_tree_kernel<%d,false,%s>" % (ns, cap, bvh)
 
 
 # ---- CPU legs: the reference algorithm on the host cores ----------------------------------------------------------
@@ -359,7 +367,7 @@ def measure_config(ctx, config_id, frames, e2e_frames, cpu_fraction, cpu_seconds
     rec = {"workload": name, "width": cd.width, "height": cd.height, "spp": cd.pre_sample_times,
            "ms_per_frame": dev_ms, "frames_timed": frames, "ray_queries_per_frame": rays,
            "value": rays / (dev_ms * 1e-3) / 1e6, "unit": "Mrays/s",
-           "samples_per_s": st["samples"] / (dev_ms * 1e-3), "kernel": kernel_name(cd, n_sph, is_lean_scene(world))}
+           "samples_per_s": st["samples"] / (dev_ms * 1e-3), "kernel": kernel_name(cd, n_sph, scene_class(world))}
     # e2e: the pipelined frame call with pinned host buffers
     bufs = [torch.empty((cd.height, cd.width, 3), dtype=torch.uint8).pin_memory().numpy() for _ in range(3)]
     eo = make_opts(seed=1, pixel_format=_abi.FMT_RGB8)
@@ -722,7 +730,7 @@ def run_ours(args, rank, local_rank, world_size):
             "clocks": clocks,
             "wall_s_timed_region": wall,
         }
-        kname = kernel_name(cams[0], n_sph, is_lean_scene(world))
+        kname = kernel_name(cams[0], n_sph, scene_class(world))
         if brute:
             flops_frame = flops_batch / B
             achieved = flops_frame / (trace_ms * 1e-3) / 1e12

@@ -184,7 +184,7 @@ struct rtrb_renderer {
     int32_t pl_index[RTRB_K_PLANES];
     int32_t has_light_tab;
   } k;
-  bool lean_scene = false;             // one light of radius 0, no textured object, exponent 2 (FrameParams::lean_scene)
+  int scene_class = 0;                 // RTRB_SCENE_CLASS_* bits (FrameParams::scene_class)
   bool small_scene = false;            // <= 32 spheres/boxes, <= 8 planes, <= 2 lights: linear-filter kernels
   std::vector<double> sph_world;       // (cx, cy, cz, R) in cull_sph[] order, FP64, for the per-frame camera table
   DevBuf<int32_t> sph_index, pl_index;
@@ -374,7 +374,11 @@ int bake_scene(rtrb_renderer* r, const rtrb_scene_desc* s) {
   {
     bool textured = false;
     for (int i = 0; i < s->n_objects; ++i) textured = textured || (s->objects[i].texture >= 0 && s->objects[i].type != RTRB_OBJ_BOX);
-    r->lean_scene = s->n_lights == 1 && s->lights[0].radius == 0.0 && !textured && s->soft_shadow_exponent == 2.0;
+    r->scene_class = 0;
+    if (s->n_lights == 1 && s->soft_shadow_exponent == 2.0) {
+      r->scene_class |= RTRB_SCENE_CLASS_ONE_LIGHT;
+      if (s->lights[0].radius == 0.0 && !textured) r->scene_class |= RTRB_SCENE_CLASS_LEAN;
+    }
   }
   for (int i = 0; i < s->n_textures; ++i) {
     const rtrb_texture_desc& t = s->textures[i];
@@ -780,7 +784,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   P.lights_f = r->lights_f.p; P.n_sph = r->n_sph; P.n_pl = r->n_pl; P.bvh = r->bvh.p;
   P.m_scene = r->m_scene; P.max_distance_f = r->max_distance_f;
   P.use_bvh = r->small_scene ? 0 : 1;
-  P.lean_scene = r->lean_scene ? 1 : 0;
+  P.scene_class = r->scene_class;
   if (r->small_scene) {
     static_assert(sizeof(r->k.light_tab) == sizeof(P.k_light_tab) && sizeof(r->k.lights) == sizeof(P.k_lights), "table layout");
     memcpy(P.k_light_tab, r->k.light_tab, sizeof(P.k_light_tab));

@@ -241,7 +241,7 @@ __device__ __forceinline__ double cover_object_exact(const FrameParams& P, const
     double dd = norm(x1 - cc);
     if (dd >= r1 + g.radius) return 0;
     double s1 = RTRB_PI * r1 * r1;
-#ifdef RTRB_LEAN_SCENE
+#ifdef RTRB_SCENE_LEAN
     // light_radius == 0.0, so r1 is a zero or a NaN (0 * inf).  Past the test above dd < R (or a comparison with a NaN
     // failed); then `dd > |R - r1|` = `dd > |R|` cannot hold (R >= 0: dd < R; R < 0: no dd >= 0 is < R; NaN: false), so
     // the partial-overlap branch (sphere.rb:37-47) is unreachable and its acos / sin / divisions are not compiled in

@@ -17,19 +17,35 @@
 // explicit fmaf().
 #pragma once
 #define RTRB_FAST_TU 1  // exact-preserving shortcuts inside the shared STRICT functions (rtrb_trace.cuh)
-// RTRB_LEAN_SCENE (rtrb_trace_fast_d1lean.cu): this translation unit only ever runs scenes with exactly one light, of
-// radius exactly 0, no textured object and soft_shadow_exponent == 2 (FrameParams::lean_scene, checked when the scene is
-// baked).  What such a scene cannot reach is compiled out - the loops over lights, the division by the number of
-// matching / lit lights (x / 1.0 == x), pow, the texture lookup and the penumbra branch of Sphere#cover_area - which
-// makes the headline kernel of config 2 13 % faster (smaller code, 128 B instead of 312 B of spills) and changes no bit.
-#ifdef RTRB_LEAN_SCENE
+// SCENE / FRAME CLASSES.  The kernels exist in several builds that differ only in what is known at compile time about
+// the scene (checked when it is baked, FrameParams::scene_class) or the frame, so that code the class cannot reach is
+// not compiled in.  Same source, same arithmetic, bit-identical results; what changes is code size, register pressure
+// and - these kernels being bound by instruction fetch and dependent issue - speed:
+//   RTRB_SCENE_ONE_LIGHT  exactly one light and soft_shadow_exponent == 2 (every BASELINE.json config): no loops over
+//                         lights, no division by the number of matching / lit lights (x / 1.0 == x), no pow.
+//                         Ray-tree kernels: configs 3 / 4 / 5 -8.6 / -9.1 / -4.3 %.
+//   RTRB_FRAME_NO_MC      monte_carlo_diffusion_times == 0: no Monte-Carlo ray code (configs 3 / 5 a further -1.6 / -4.9 %).
+//   RTRB_SCENE_LEAN       ONE_LIGHT plus: the light's radius is exactly 0 (hard shadows) and no object is textured: no
+//                         texture lookup, no penumbra branch in Sphere#cover_area.  Depth-1 kernels (config 2): -13 %.
+#ifdef RTRB_SCENE_LEAN
+#define RTRB_SCENE_ONE_LIGHT 1
+#endif
+#ifdef RTRB_SCENE_ONE_LIGHT
 #define RTRB_NL(P) 1
-#define RTRB_TEX(M) false
 #define RTRB_EXP(P) 2.0
 #else
 #define RTRB_NL(P) (P).n_lights
-#define RTRB_TEX(M) ((M).tex != nullptr)
 #define RTRB_EXP(P) (P).soft_shadow_exponent
+#endif
+#ifdef RTRB_SCENE_LEAN
+#define RTRB_TEX(M) false
+#else
+#define RTRB_TEX(M) ((M).tex != nullptr)
+#endif
+#ifdef RTRB_FRAME_NO_MC
+#define RTRB_MC(P) 0
+#else
+#define RTRB_MC(P) (P).mc
 #endif
 #include "rtrb_trace.cuh"
 
@@ -767,7 +783,7 @@ template <int MAXS, bool BVH, bool BOX>
 __device__ __forceinline__ void item_phase_b(const FrameParams& P, const StackItem& it, const int best_i, const HitRec& bh,
                                              StackItem* stack, int& sp, d3& sum, ThreadCtx& ctx, uint32_t pixel,
                                              uint32_t sample) {
-  const uint32_t K = (uint32_t)(P.mc + 2);
+  const uint32_t K = (uint32_t)(RTRB_MC(P) + 2);
   constexpr bool KT = !BVH && MAXS == 1;
   {
     const d3 o = mk(it.ox, it.oy, it.oz), d = mk(it.dx, it.dy, it.dz), att = mk(it.ax, it.ay, it.az);
@@ -872,17 +888,17 @@ __device__ __forceinline__ void item_phase_b(const FrameParams& P, const StackIt
       }
     }
     if (n_lit == 0) {
-      if (MAXS == 1 && P.mc > 0 && ctx.detail) ctx.c[RTRB_CNT_MC] += P.mc;  // spawned, born dead
-      if (MAXS > 1 && P.mc > 0) {
-        if (sp + P.mc > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; return; }
-        const d3 att_pt = ld3(M.diffuse) / (double)P.mc;
+      if (MAXS == 1 && RTRB_MC(P) > 0 && ctx.detail) ctx.c[RTRB_CNT_MC] += RTRB_MC(P);  // spawned, born dead
+      if (MAXS > 1 && RTRB_MC(P) > 0) {
+        if (sp + RTRB_MC(P) > MAXS) { ctx.status |= RTRB_ST_STACK_OVERFLOW; return; }
+        const d3 att_pt = ld3(M.diffuse) / (double)RTRB_MC(P);
         const d3 a2 = att * att_pt;
         const bool mc_alive = depth_ok && !(sumsq(a2) < 0.99e-8);
         const d3 vv = a_vertical_vector(n, ctx);
         if (mc_alive || sumsq(vv) == 0) {
           const d3 leftv = normalize(vv, ctx);
           const d3 upv = cross(nn, leftv);
-          for (int m = 0; m < P.mc; ++m) {
+          for (int m = 0; m < RTRB_MC(P); ++m) {
             uint32_t child = it.path * K + (uint32_t)(2 + m);
             uint32_t c0 = pixel, c1 = sample, c2 = child, c3 = 1u;
             philox4x32_10(P.key0, P.key1, c0, c1, c2, c3);
@@ -895,7 +911,7 @@ __device__ __forceinline__ void item_phase_b(const FrameParams& P, const StackIt
             s.depth = it.depth - 1; s.path = child;
           }
         }
-        if (ctx.detail) ctx.c[RTRB_CNT_MC] += P.mc;
+        if (ctx.detail) ctx.c[RTRB_CNT_MC] += RTRB_MC(P);
       }
     } else {
       RTRB_COUNT(ctx, RTRB_CNT_LOCAL);

@@ -18,6 +18,8 @@
 #define RTRB_APEX_MAX 32              // linear-filter scenes (<= 32 spheres) get apex tables, see FrameParams
 #define RTRB_K_PLANES 8               // ... have at most this many planes
 #define RTRB_K_LIGHTS 2               // ... and at most this many lights (anything larger runs the BVH kernels)
+#define RTRB_SCENE_CLASS_ONE_LIGHT 1
+#define RTRB_SCENE_CLASS_LEAN 2
 #define RTRB_TREE_MIN_BLOCK 128        // smallest CTA the ray-tree kernels are launched with (the largest is 512): a
                                       // pre_sample_times that divides it has every sample of a pixel in one CTA
 
@@ -104,9 +106,10 @@ struct FrameParams {
   const struct BvhNode* bvh;   // sphere BVH over cull_sph[] (rtrb_bvh.h); node 0 = root
   int32_t n_sph, n_pl;
   int32_t use_bvh;             // > RTRB_BVH_MIN_SPHERES spheres: BVH kernels; else the linear-scan kernels
-  int32_t lean_scene;          // 1: ONE light of radius exactly 0 (hard shadows), no textured object, soft_shadow_exponent
-                               // == 2: depth-1 frames run kernels compiled without the code such a scene cannot reach
-                               // (rtrb_trace_fast_d1lean.cu); results are the generic kernels' bit for bit
+  int32_t scene_class;         // what is known about the scene (rtrb_trace_fast.cuh, "scene / frame classes"):
+                               // bit 0 = exactly one light and soft_shadow_exponent == 2; bit 1 = that and: the
+                               // light's radius is exactly 0 and no object is textured.  Selects kernel builds
+                               // without the code the class cannot reach; results are the generic kernels' bit for bit
   // Apex tables (linear-filter scenes only): rays that pass through a known point A — primary rays
   // through the lens centre (within aperture_radius), shadow probes through their light — test sphere k
   // with b = v.u, survive unless b*b < Kq, where (v, Kq) = (C - A, |v|^2 - (R + margins)^2 - slack)

@@ -26,15 +26,16 @@ def test_config_record_is_the_workload_only_and_identical_for_both_arms():
 
 def test_kernel_name_follows_the_dispatch():
     from raytracing_rb_b200 import Camera
-    for cid, want in ((2, "rtrb_fast_lean::trace_pre_fast_kernel<1,false,false>"),
-                      (3, "rtrb_fast::trace_pre_tree_kernel<10,false,false>"),
-                      (4, "rtrb_fast::trace_pre_tree_kernel<10,false,false>"),
-                      (5, "rtrb_fast::trace_pre_tree_kernel<10,false,true>")):
+    for cid, klass, want in ((2, "lean", "rtrb_fast_lean::trace_pre_fast_kernel<1,false,false>"),
+                             (1, "one_light", "rtrb_fast_l1::trace_pre_tree_kernel<10,false,false>"),
+                             (3, "one_light", "rtrb_fast_l1n::trace_pre_tree_kernel<10,false,false>"),
+                             (4, "one_light", "rtrb_fast_l1::trace_pre_tree_kernel<10,false,false>"),
+                             (5, "one_light", "rtrb_fast_l1n::trace_pre_tree_kernel<10,false,true>")):
         world, cdoc, _ = bench.workload(cid)
         cd = Camera(world, cdoc).camera_desc()
         n_sph = sum(1 for o in world.world_objects if type(o).__name__ in ("Sphere", "Box"))
-        assert bench.kernel_name(cd, n_sph, bench.is_lean_scene(world)) == want
-    assert bench.is_lean_scene(bench.workload(2)[0]) and not bench.is_lean_scene(bench.workload(3)[0])
+        assert bench.scene_class(world) == klass
+        assert bench.kernel_name(cd, n_sph, klass) == want
 
 
 def test_cpu_window_is_a_centred_full_height_strip():
