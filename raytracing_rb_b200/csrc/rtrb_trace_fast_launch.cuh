@@ -18,7 +18,11 @@ namespace RTRB_FAST_NS {
 //                                3.57 ms and config 5: 5.13 / 4.61 / 4.24 ms with 128 / 256 / 512 threads; config 3:
 //                                3.87 / 3.44 / 3.52), 128 threads on small frames
 #ifndef RTRB_FAST_MIN_BLOCKS
+#ifdef RTRB_SCENE_LEAN
+#define RTRB_FAST_MIN_BLOCKS 8  // lean depth-1 kernel (124 registers unconstrained): 0.086 / 0.080 / 0.078 / 0.076 / 0.078 / 0.088 ms
+#else                           // on config 2 at 4 / 5 / 7 / 8 / 10 / 12 CTAs per SM (124 / 96 / 72 / 64 / 48 / 40 registers)
 #define RTRB_FAST_MIN_BLOCKS 5
+#endif
 #endif
 constexpr int kFastBlock = 128, kFastMinBlocks = RTRB_FAST_MIN_BLOCKS, kExtraMinBlocks = 4, kTreeBlock = 512, kTreeMinBlocks = 1;
 
