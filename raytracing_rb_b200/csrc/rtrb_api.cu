@@ -157,7 +157,7 @@ struct FrameCtl {
 
 struct rtrb_renderer {
   int device = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr, ctl_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t push_ev = nullptr, push_done_ev = nullptr;  // rtrb_peer_push ordering (no timing)
   FrameCtl main_ctl;       // synchronous calls
   FrameCtl pipe_ctl[RTRB_PIPE_SLOTS];  // rtrb_submit / rtrb_wait frame slots
@@ -284,6 +284,11 @@ __global__ void __launch_bounds__(256) resolve_extra_kernel(const __grid_constan
     ax = (ax * fp + cx) / fm; ay = (ay * fp + cy) / fm; az = (az * fp + cz) / fm;
     write_pixel(P, x, y, ax, ay, az);
   }
+}
+
+// Frame control block -> its pinned host mirror by direct stores (zero-copy over PCIe): see rtrb_submit.
+__global__ void publish_ctl_kernel(unsigned long long* host, const unsigned long long* dev, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) host[i] = dev[i];
 }
 
 __global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
@@ -1019,7 +1024,6 @@ int rtrb_renderer_create(const rtrb_scene_desc* scene, int device, rtrb_renderer
   cudaError_t ce;
   if ((ce = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (ce = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (ce = cudaStreamCreateWithFlags(&r->ctl_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (ce = cudaEventCreateWithFlags(&r->push_ev, cudaEventDisableTiming)) != cudaSuccess ||
       (ce = cudaEventCreateWithFlags(&r->push_done_ev, cudaEventDisableTiming)) != cudaSuccess ||
       (ce = (cudaError_t)r->main_ctl.init()) != cudaSuccess) {
@@ -1048,7 +1052,6 @@ int rtrb_renderer_destroy(rtrb_renderer* r) {
   if (r->push_done_ev) cudaEventDestroy(r->push_done_ev);
   if (r->stream) cudaStreamDestroy(r->stream);
   if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
-  if (r->ctl_stream) cudaStreamDestroy(r->ctl_stream);
   delete r;
   return RTRB_OK;
 }
@@ -1134,11 +1137,14 @@ int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   CUDA_TRY(cudaStreamWaitEvent(r->copy_stream, fc.ev1, 0));
   CUDA_TRY(cudaMemcpyAsync(rgba_host, tg.rgba, bytes, cudaMemcpyDeviceToHost, r->copy_stream));
   CUDA_TRY(cudaEventRecord(fc.copied, r->copy_stream));
-  // the 200-byte control block travels on its own stream: behind the frame on copy_stream its fixed
-  // latency (~10 us) would be added to every frame of a PCIe-bound sequence
-  CUDA_TRY(cudaStreamWaitEvent(r->ctl_stream, fc.ev1, 0));
-  CUDA_TRY(cudaMemcpyAsync(fc.h, fc.d.p, RTRB_FCB_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->ctl_stream));
-  CUDA_TRY(cudaEventRecord(fc.ctl_copied, r->ctl_stream));
+  // The 1.3 KB control block does not go through the copy engine at all: a one-block kernel behind the frame's kernels
+  // stores it straight into the pinned (device-mapped) host mirror.  As a DMA of its own - even on its own stream - it
+  // sat between the 6.2 MB frame copies of a PCIe-bound sequence and cost 6 % of the frame rate (8 057 -> 8 540 frames/s
+  // on config 2); behind the frame on the copy stream it cost 14 % (round 1).
+  publish_ctl_kernel<<<1, 256, 0, r->stream>>>(fc.h, fc.d.p, RTRB_FCB_WORDS);
+  CUDA_TRY(cudaGetLastError());
+  g_launches++;
+  CUDA_TRY(cudaEventRecord(fc.ctl_copied, r->stream));
   // (the slot is reused only after rtrb_wait has host-synchronised on `copied`, so no stream wait is needed)
   fc.in_flight = true;
   fc.ticket = ticket;
