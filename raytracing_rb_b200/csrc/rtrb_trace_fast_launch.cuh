@@ -17,6 +17,9 @@ namespace RTRB_FAST_NS {
 //                                512 threads x 1 CTA per SM on frames of more than a few waves (config 4: 4.44 / 3.78 /
 //                                3.57 ms and config 5: 5.13 / 4.61 / 4.24 ms with 128 / 256 / 512 threads; config 3:
 //                                3.87 / 3.44 / 3.52), 128 threads on small frames
+#ifndef RTRB_TREE_BLOCK
+#define RTRB_TREE_BLOCK 512
+#endif
 #ifndef RTRB_FAST_MIN_BLOCKS
 #ifdef RTRB_SCENE_LEAN
 #define RTRB_FAST_MIN_BLOCKS 8  // lean depth-1 kernel (124 registers unconstrained): 0.086 / 0.080 / 0.078 / 0.076 / 0.078 / 0.088 ms
@@ -24,7 +27,7 @@ namespace RTRB_FAST_NS {
 #define RTRB_FAST_MIN_BLOCKS 5
 #endif
 #endif
-constexpr int kFastBlock = 128, kFastMinBlocks = RTRB_FAST_MIN_BLOCKS, kExtraMinBlocks = 4, kTreeBlock = 512, kTreeMinBlocks = 1;
+constexpr int kFastBlock = 128, kFastMinBlocks = RTRB_FAST_MIN_BLOCKS, kExtraMinBlocks = 4, kTreeBlock = RTRB_TREE_BLOCK, kTreeMinBlocks = 1;
 
 template <int MAXS, bool DETAIL, bool BVH>
 __global__ void __launch_bounds__(kFastBlock, kFastMinBlocks) trace_pre_fast_kernel(const __grid_constant__ FrameParams P) {
