@@ -226,10 +226,13 @@ __device__ __forceinline__ CoverRay make_cover_ray(d3 target, const DevLight& L)
 // cover_area of ONE object, exactly as the reference evaluates it:
 // Sphere#cover_area (sphere.rb:28-57) / WorldObject#cover_area (world_object.rb:41-49).
 // BOX = false compiles the box branch out (kernels specialised for sphere/plane scenes).
-template <bool BOX = true>
+// KIND tells what the caller already knows about g.type, so that the other branches are not compiled into its loop
+// (the sphere branch with its penumbra code is 800 instructions): 0 = anything (the reference's own scan), 1 = a sphere
+// or a box (an entry of the sphere filter), 2 = a plane.
+template <bool BOX = true, int KIND = 0>
 __device__ __forceinline__ double cover_object_exact(const FrameParams& P, const DevGeom& g, const CoverRay& c,
                                                      double light_radius, ThreadCtx& ctx) {
-  if (g.type == RTRB_OBJ_SPHERE) {
+  if (KIND != 2 && g.type == RTRB_OBJ_SPHERE) {
     RTRB_COUNT(ctx, RTRB_CNT_COV_SPH);
     HitRec h;
     int factor = 0;
@@ -260,7 +263,7 @@ __device__ __forceinline__ double cover_object_exact(const FrameParams& P, const
     if (r1 > g.radius) return factor * RTRB_PI * g.radius * g.radius / s1;
     return factor;
   }
-  if constexpr (BOX) {
+  if constexpr (BOX && KIND != 2) {
     if (g.type == RTRB_OBJ_BOX) {  // WorldObject#cover_area (world_object.rb:41-49) through Box#intersect
       RTRB_COUNT(ctx, RTRB_CNT_COV_BOX);
       HitRec h;
@@ -271,6 +274,7 @@ __device__ __forceinline__ double cover_object_exact(const FrameParams& P, const
       return 0;
     }
   }
+  if constexpr (KIND == 1) return 0;  // (unreachable: the sphere filter only lists spheres and boxes)
   RTRB_COUNT(ctx, RTRB_CNT_COV_PL);
   HitRec h;
   double den;

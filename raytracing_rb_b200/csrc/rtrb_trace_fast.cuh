@@ -440,7 +440,8 @@ __device__ __forceinline__ double lit_area_bvh(const FrameParams& P, d3 target, 
       }
     }
     RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-    total -= cover_object_exact<BOX>(P, P.geom[best_idx], c, L.radius, ctx);
+    if (best_k >= 0) total -= cover_object_exact<BOX, 1>(P, P.geom[best_idx], c, L.radius, ctx);
+    else total -= cover_object_exact<BOX, 2>(P, P.geom[best_idx], c, L.radius, ctx);
   }
   return fmax(total, 0.0);
 }
@@ -622,11 +623,11 @@ __device__ __forceinline__ double lit_area_linear(const FrameParams& P, d3 targe
         have_n = true;
       }
       RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-      total -= cover_object_exact<BOX>(P, P.geom[is], c, L.radius, ctx);
+      total -= cover_object_exact<BOX, 1>(P, P.geom[is], c, L.radius, ctx);
     } else {
       qm &= qm - 1u;
       RTRB_COUNT(ctx, RTRB_CNT_EXACT);
-      total -= cover_object_exact<BOX>(P, P.geom[iq], c, L.radius, ctx);
+      total -= cover_object_exact<BOX, 2>(P, P.geom[iq], c, L.radius, ctx);
     }
   }
   return fmax(total, 0.0);
