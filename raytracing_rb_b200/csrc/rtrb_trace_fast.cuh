@@ -1008,13 +1008,16 @@ __device__ __forceinline__ d3 trace_sample_fast_lockstep(const FrameParams& P, d
   bool first = true, have = active;
   *primary_hit = -1;
   if (active) ctx.max_stack = max(ctx.max_stack, 1u);
+  const bool mid_barrier = BVH && P.pre < 32;
   while (__syncthreads_or(have ? 1 : 0)) {
     HitRec bh;
     int best_i = -1;
     if (have) best_i = item_phase_a<MAXS, BVH, BOX>(P, it, sum, ctx, first, primary_hit, bh);
-    // phase boundary: with the BVH filter the whole CTA also moves from intersection to shading together (config 5:
-    // 4.22 -> 3.82 ms); with the linear filter the second barrier costs more than it saves (config 3: +3 %)
-    if constexpr (BVH) __syncthreads();
+    // phase boundary: with the BVH filter the whole CTA also moves from intersection to shading together when a warp
+    // holds several pixels (config 5 at 4 spp: 3.90 -> 3.53 ms); with a whole warp on one pixel (>= 32 spp) the warps are
+    // even enough without it (config 5 at 64 spp: 956 -> 944 ms without), and with the linear filter the second
+    // barrier costs more than it saves (config 3: +3 %)
+    if constexpr (BVH) { if (mid_barrier) __syncthreads(); }
     if (have) {
       if (best_i >= 0) item_phase_b<MAXS, BVH, BOX>(P, it, best_i, bh, stack, sp, sum, ctx, pixel, sample);
       first = false;
