@@ -27,7 +27,7 @@ namespace RTRB_FAST_NS {
 #define RTRB_FAST_MIN_BLOCKS 5
 #endif
 #endif
-constexpr int kFastBlock = 128, kFastMinBlocks = RTRB_FAST_MIN_BLOCKS, kExtraMinBlocks = 4, kTreeBlock = RTRB_TREE_BLOCK, kTreeMinBlocks = 1;
+constexpr int kFastBlock = 128, kFastMinBlocks = RTRB_FAST_MIN_BLOCKS, kExtraMinBlocks = 4, kTreeBlock = RTRB_TREE_BLOCK, kTreeMinBlocks = 512 / RTRB_TREE_BLOCK > 0 ? 512 / RTRB_TREE_BLOCK : 1;
 
 template <int MAXS, bool DETAIL, bool BVH>
 __global__ void __launch_bounds__(kFastBlock, kFastMinBlocks) trace_pre_fast_kernel(const __grid_constant__ FrameParams P) {
