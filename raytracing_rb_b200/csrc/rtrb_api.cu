@@ -129,7 +129,8 @@ struct DevBuf {
 #define RTRB_PIPE_SLOTS 4  // frames that may be in flight between rtrb_submit and rtrb_wait
 struct FrameCtl {
   DevBuf<unsigned long long> d;
-  unsigned long long* h = nullptr;  // pinned host mirror
+  unsigned long long* h = nullptr;  // pinned host mirror (mapped into the device's address space)
+  unsigned long long* h_dev = nullptr;  // ... and the address the device stores to (publish_ctl_kernel)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr, copied = nullptr, ctl_copied = nullptr;
   DevBuf<uint8_t> rgba;             // pipeline slots own a framebuffer; the main slot uses rtrb_renderer::rgba
   // facts of the frame in flight, needed to finish its stats later
@@ -140,7 +141,8 @@ struct FrameCtl {
   int init() {
     cudaError_t e;
     if ((e = d.ensure(RTRB_FCB_WORDS)) != cudaSuccess) return (int)e;
-    if ((e = cudaMallocHost((void**)&h, RTRB_FCB_WORDS * sizeof(unsigned long long))) != cudaSuccess) return (int)e;
+    if ((e = cudaHostAlloc((void**)&h, RTRB_FCB_WORDS * sizeof(unsigned long long), cudaHostAllocMapped)) != cudaSuccess) return (int)e;
+    if ((e = cudaHostGetDevicePointer((void**)&h_dev, h, 0)) != cudaSuccess) return (int)e;
     cudaEvent_t* evs[6] = {&ev0, &ev1, &evt0, &evt1, &copied, &ctl_copied};
     for (auto ev : evs)
       if ((e = cudaEventCreate(ev)) != cudaSuccess) return (int)e;
@@ -149,7 +151,7 @@ struct FrameCtl {
   void destroy() {
     d.release(); rgba.release();
     if (h) cudaFreeHost(h);
-    h = nullptr;
+    h = nullptr; h_dev = nullptr;
     cudaEvent_t* evs[6] = {&ev0, &ev1, &evt0, &evt1, &copied, &ctl_copied};
     for (auto ev : evs) { if (*ev) cudaEventDestroy(*ev); *ev = nullptr; }
   }
@@ -1141,7 +1143,7 @@ int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   // stores it straight into the pinned (device-mapped) host mirror.  As a DMA of its own - even on its own stream - it
   // sat between the 6.2 MB frame copies of a PCIe-bound sequence and cost 6 % of the frame rate (8 057 -> 8 540 frames/s
   // on config 2); behind the frame on the copy stream it cost 14 % (round 1).
-  publish_ctl_kernel<<<1, 256, 0, r->stream>>>(fc.h, fc.d.p, RTRB_FCB_WORDS);
+  publish_ctl_kernel<<<1, 256, 0, r->stream>>>(fc.h_dev, fc.d.p, RTRB_FCB_WORDS);
   CUDA_TRY(cudaGetLastError());
   g_launches++;
   CUDA_TRY(cudaEventRecord(fc.ctl_copied, r->stream));
