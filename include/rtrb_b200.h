@@ -65,9 +65,17 @@ enum {
 /* ---- rtrb_render_opts.pixel_format: layout of the 8-bit frame -------------------------------- */
 enum {
   RTRB_FMT_RGBA8 = 0, /* H*W*4 bytes, alpha = 255: what array_to_color builds (camera.rb:153-156) */
-  RTRB_FMT_RGB8 = 1   /* H*W*3 bytes: alpha is the constant 255, so it need not cross PCIe; the caller
+  RTRB_FMT_RGB8 = 1,  /* H*W*3 bytes: alpha is the constant 255, so it need not cross PCIe; the caller
                          (Camera#render_cuda) re-inserts it when it fills the PNG canvas */
+  RTRB_FMT_PNG_RGB8 = 2 /* H rows of 1 + 3*W bytes: the PNG filter-type byte 0 ("None") followed by the row's RGB8
+                         pixels, i.e. exactly the byte stream a PNG encoder deflates into IDAT for an 8-bit RGB image
+                         (what Camera#save_image, camera.rb:36-39, produces through the png gem): the host only runs
+                         zlib over the buffer and frames the chunks */
 };
+/* bytes of one 8-bit frame in `format` */
+#define RTRB_FRAME_BYTES(width, height, format) \
+  ((format) == RTRB_FMT_RGBA8 ? (size_t)(width) * (height) * 4 : (format) == RTRB_FMT_RGB8 ? (size_t)(width) * (height) * 3 \
+                                                               : (size_t)(height) * ((size_t)(width) * 3 + 1))
 
 /* ---- rtrb_render_opts.skip_outputs ----------------------------------------------------------- */
 enum { RTRB_SKIP_RGB = 1, RTRB_SKIP_HIT = 2 };
@@ -208,8 +216,8 @@ int rtrb_renderer_destroy(rtrb_renderer* r);
 int rtrb_render_device(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render_opts* opts,
                        rtrb_stats* stats_out);
 
-/* Copies the last frame to HOST buffers. rgba: H*W*4 bytes (H*W*3 when the frame was rendered with
- * RTRB_FMT_RGB8), row = y, column = x (camera.rb:98,105);
+/* Copies the last frame to HOST buffers. rgba: RTRB_FRAME_BYTES(W, H, pixel_format) bytes (H*W*4 for the default
+ * RTRB_FMT_RGBA8), row = y, column = x (camera.rb:98,105);
  * rgb_or_null: H*W*3 doubles = render_at's unclamped `color`; hit_or_null: H*W int32 primary hit
  * ids (index in world_objects, -1 miss, -2 highlight-terminated, -3 pixel not rendered). */
 int rtrb_download(rtrb_renderer* r, uint8_t* rgba, double* rgb_or_null, int32_t* hit_or_null);

@@ -6,7 +6,7 @@ ConfigurableObject, Vec3); the hot path is hand-written CUDA for sm_100a in csrc
 the C ABI of include/rtrb_b200.h.  No CPU fallback exists."""
 from . import _abi
 from ._abi import PREC_DEFAULT, PREC_FAST64, PREC_STRICT, RNG_CTR, RNG_MT
-from .camera import Camera, write_png
+from .camera import Camera, write_png, write_png_scanlines
 from .configurable_object import ConfigurableObject
 from .lights import Light, SpotLight
 from .objects import Box, Plane, Sphere, WorldObject
@@ -19,6 +19,6 @@ from .world import World
 __all__ = [
     "Camera", "World", "Sphere", "Plane", "Box", "WorldObject", "Light", "SpotLight", "Texture", "Vec3",
     "ConfigurableObject", "Renderer", "Frame", "make_opts", "render_multi", "measure_fma_peak",
-    "device_count", "deal_frames", "ipc_open", "ipc_close", "write_png", "tile_partition",
+    "device_count", "deal_frames", "ipc_open", "ipc_close", "write_png", "write_png_scanlines", "tile_partition",
     "PREC_STRICT", "PREC_FAST64", "PREC_DEFAULT", "RNG_CTR", "RNG_MT",
 ]

@@ -13,7 +13,7 @@ ST_STACK_OVERFLOW = 1 << 3
 ST_NAN_TO_INT = 1 << 4
 
 OBJ_PLANE, OBJ_SPHERE, OBJ_BOX = 0, 1, 2
-FMT_RGBA8, FMT_RGB8 = 0, 1
+FMT_RGBA8, FMT_RGB8, FMT_PNG_RGB8 = 0, 1, 2
 RNG_CTR, RNG_MT = 0, 1
 PREC_STRICT, PREC_FAST64 = 0, 1
 PREC_DEFAULT = PREC_FAST64

@@ -32,6 +32,20 @@ def write_png(path, rgba):
         f.write(chunk(b"IEND", b""))
 
 
+def write_png_scanlines(path, scanlines, width, height):
+    """PNG (8-bit RGB) from RTRB_FMT_PNG_RGB8 scanlines: the device already laid the rows out the way IDAT wants them
+    (filter byte + pixels), so the host only deflates and frames the chunks."""
+    def chunk(tag, data):
+        c = struct.pack(">I", len(data)) + tag + data
+        return c + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n")
+        f.write(chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, 8, 2, 0, 0, 0)))
+        f.write(chunk(b"IDAT", zlib.compress(np.ascontiguousarray(scanlines).tobytes(), 6)))
+        f.write(chunk(b"IEND", b""))
+
+
 class Camera(ConfigurableObject):
     # camera.rb:17-24 accessors
     position = up = front = None

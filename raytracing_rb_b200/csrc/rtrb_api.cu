@@ -219,7 +219,7 @@ struct rtrb_renderer {
   // last frame
   int last_w = 0, last_h = 0;
   bool last_has_rgb = false, last_has_hit = false, last_rgba_own = true;
-  int last_bpp = 4;
+  int last_format = RTRB_FMT_RGBA8;
   cudaStream_t last_stream = nullptr;
   bool timing_valid = false;
 };
@@ -679,7 +679,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   }
   if (opts.precision != RTRB_PREC_STRICT && opts.precision != RTRB_PREC_FAST64)
     return fail(RTRB_ERR_INVALID, "unknown precision mode %d", opts.precision);
-  if (opts.pixel_format != RTRB_FMT_RGBA8 && opts.pixel_format != RTRB_FMT_RGB8)
+  if (opts.pixel_format != RTRB_FMT_RGBA8 && opts.pixel_format != RTRB_FMT_RGB8 && opts.pixel_format != RTRB_FMT_PNG_RGB8)
     return fail(RTRB_ERR_INVALID, "unknown pixel format %d", opts.pixel_format);
   const int W = cam->width, H = cam->height;
   int x0 = opts.x0, y0 = opts.y0, x1 = opts.x1, y1 = opts.y1;
@@ -926,7 +926,7 @@ int render_impl(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   r->last_has_rgb = tg.rgb == r->rgb.p && tg.rgb != nullptr;
   r->last_has_hit = tg.hit == r->hit.p && tg.hit != nullptr;
   r->last_stream = stream;
-  r->last_bpp = opts.pixel_format == RTRB_FMT_RGB8 ? 3 : 4;
+  r->last_format = opts.pixel_format;
 
   // facts needed to finish the stats once the control block has been copied back
   fc.W = W; fc.H = H; fc.S = S; fc.E = E; fc.n_tiles = n_tiles; fc.detail = P.count_detail != 0;
@@ -1071,7 +1071,7 @@ int rtrb_download(rtrb_renderer* r, uint8_t* rgba, double* rgb_or_null, int32_t*
   size_t px = (size_t)r->last_w * r->last_h;
   if (rgba) {
     if (!r->last_rgba_own) return fail(RTRB_ERR_INVALID, "the last frame was written to rgba_device_out, not to the renderer's framebuffer");
-    CUDA_TRY(cudaMemcpyAsync(rgba, r->rgba.p, px * (size_t)r->last_bpp, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(rgba, r->rgba.p, RTRB_FRAME_BYTES(r->last_w, r->last_h, r->last_format), cudaMemcpyDeviceToHost, s));
   }
   if (rgb_or_null) {
     if (!r->last_has_rgb) return fail(RTRB_ERR_INVALID, "the last frame kept no float RGB");
@@ -1117,8 +1117,7 @@ int rtrb_submit(rtrb_renderer* r, const rtrb_camera_desc* cam, const rtrb_render
   const unsigned ticket = r->next_ticket;
   FrameCtl& fc = r->pipe_ctl[ticket % RTRB_PIPE_SLOTS];
   if (fc.in_flight) return fail(RTRB_ERR_INVALID, "%d frames are already in flight: call rtrb_wait first", RTRB_PIPE_SLOTS);
-  const size_t bpp = (opts && opts->pixel_format == RTRB_FMT_RGB8) ? 3 : 4;
-  const size_t bytes = (size_t)cam->width * cam->height * bpp;
+  const size_t bytes = RTRB_FRAME_BYTES(cam->width, cam->height, opts ? opts->pixel_format : RTRB_FMT_RGBA8);
   const size_t slot_bytes = (size_t)cam->width * cam->height * 4;
   if (cam->width > 0 && cam->height > 0 && fc.rgba.n < slot_bytes) {
     CUDA_TRY(fc.rgba.ensure(slot_bytes));
@@ -1325,7 +1324,7 @@ int rtrb_render_multi(rtrb_renderer* const* renderers, int n, const rtrb_camera_
   root->last_w = cam->width; root->last_h = cam->height;
   root->last_has_rgb = want_rgb; root->last_has_hit = want_hit; root->last_rgba_own = true;
   root->last_stream = root->stream;
-  root->last_bpp = base.pixel_format == RTRB_FMT_RGB8 ? 3 : 4;
+  root->last_format = base.pixel_format;
   std::string keep = g_last_error;
   rc = rtrb_download(root, rgba, rgb_or_null, hit_or_null);
   if (rc) return rc;

@@ -604,6 +604,14 @@ __device__ __forceinline__ uint8_t quantise_u8(double c) {
 __device__ __forceinline__ void write_pixel(const FrameParams& P, int x, int y, double r, double g, double b) {
   size_t px = (size_t)y * P.width + x;
   if (P.rgb) { P.rgb[px * 3 + 0] = r; P.rgb[px * 3 + 1] = g; P.rgb[px * 3 + 2] = b; }
+  if (P.pixel_format == RTRB_FMT_PNG_RGB8) {
+    // PNG scanline: filter-type byte 0, then the row's RGB8 pixels (the stream a PNG encoder deflates into IDAT)
+    uint8_t* row = P.rgba + (size_t)y * ((size_t)P.width * 3 + 1);
+    if (x == 0) row[0] = 0;
+    uint8_t* o = row + 1 + (size_t)x * 3;
+    o[0] = quantise_u8(r); o[1] = quantise_u8(g); o[2] = quantise_u8(b);
+    return;
+  }
   if (P.pixel_format == RTRB_FMT_RGB8) {
     // alpha is the constant 255 (camera.rb:155): three byte stores; a warp's 8x4 pixel block is four
     // 24-byte runs which the L2 merges before the frame leaves over PCIe / NVLink

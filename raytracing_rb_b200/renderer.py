@@ -81,8 +81,11 @@ class Renderer:
         """The frame-level call the Ruby shim binds (host buffers in, host buffers out)."""
         opts = opts or make_opts()
         H, W = cam.height, cam.width
-        channels = 3 if opts.pixel_format == _abi.FMT_RGB8 else 4
-        rgba = out_rgba if out_rgba is not None else np.empty((H, W, channels), np.uint8)
+        if opts.pixel_format == _abi.FMT_PNG_RGB8:   # H scanlines of (filter byte 0, W x RGB8): IDAT's payload before deflate
+            shape = (H, W * 3 + 1)
+        else:
+            shape = (H, W, 3 if opts.pixel_format == _abi.FMT_RGB8 else 4)
+        rgba = out_rgba if out_rgba is not None else np.empty(shape, np.uint8)
         rgb = np.empty((H, W, 3), np.float64) if want_rgb else None
         hit = np.empty((H, W), np.int32) if want_hit else None
         st = _abi.Stats()

@@ -134,3 +134,23 @@ def test_in_cta_resolve_equals_the_sample_buffer_path(oracle_mod, pre, mx, thr):
         assert a.stats[k] == b.stats[k] == ref.stats[k], k
     if thr == 0.0:
         assert b.stats["adaptive_pixels"] == 120 * 68
+
+
+def test_png_scanline_format_is_idat_ready(tmp_path):
+    """RTRB_FMT_PNG_RGB8: H scanlines of (filter byte 0, W x RGB8) - the stream Camera#save_image's encoder deflates
+    (camera.rb:36-39).  Deflated and framed by the host, the file decodes to the RGB8 frame; blocking and pipelined."""
+    import torch
+    from PIL import Image
+    from raytracing_rb_b200 import write_png_scanlines
+    world, cam = load_scene(3, width=200, height=120)
+    r, c = cam.renderer(), cam.camera_desc()
+    rgb = r.render(c, make_opts(seed=4, pixel_format=_abi.FMT_RGB8), want_rgb=False, want_hit=False).rgba
+    rows = r.render(c, make_opts(seed=4, pixel_format=_abi.FMT_PNG_RGB8), want_rgb=False, want_hit=False).rgba
+    assert rows.shape == (120, 200 * 3 + 1) and not rows[:, 0].any()
+    assert np.array_equal(rows[:, 1:].reshape(120, 200, 3), rgb)
+    path = tmp_path / "frame.png"
+    write_png_scanlines(str(path), rows, 200, 120)
+    assert np.array_equal(np.asarray(Image.open(path).convert("RGB")), rgb)
+    buf = torch.full((120, 601), 7, dtype=torch.uint8).pin_memory().numpy()
+    r.wait(r.submit(c, buf, make_opts(seed=4, pixel_format=_abi.FMT_PNG_RGB8)))
+    assert np.array_equal(buf, rows)
