@@ -740,6 +740,7 @@ def run_ours(args, rank, local_rank, world_size):
                 "traffic": ncu_traffic_bytes() if args.config == 2 and not args.small else None,
                 "peak_source": "measured in this job: dependent-free DFMA microbenchmark (rtrb_measure_fma_peak)",
                 "peak_fp32": peak32, "algorithmic_flops_per_launch": flops_frame, "kernel_ms": trace_ms,
+                "ncu": ncu_record() if args.config == 2 and not args.small else None,
                 "hbm": {"algorithmic_bytes_per_launch": frame_bytes, "peak_gbs": measured_hbm_gbs(),
                         "achieved_gbs": frame_bytes / (trace_ms * 1e-3) / 1e9},
                 "note": "FP-issue bound path (SURVEY.md 8d): HBM traffic is the framebuffer write only; rank 0's kernel and counters",
@@ -765,16 +766,22 @@ def run_ours(args, rank, local_rank, world_size):
         dist.destroy_process_group()
 
 
-def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the trace kernel, per launch, from the committed
-    `ncu --set full` capture of this workload (profiles/r2_traffic.json, else r1); None when absent."""
+def ncu_record():
+    """Figures of the trace kernel from the committed `ncu --set full` capture of this workload
+    (profiles/r2_traffic.json, written from profiles/r2_ncu_config2_fast.txt): DRAM bytes per launch, issue-slot and pipe
+    utilisation.  None when absent."""
     for name in ("r2_traffic.json", "r1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
-                return json.load(f)["dram_bytes_per_launch"]
+                return json.load(f)
         except Exception:
             continue
     return None
+
+
+def ncu_traffic_bytes():
+    r = ncu_record()
+    return r["dram_bytes_per_launch"] if r else None
 
 
 def measured_hbm_gbs():
